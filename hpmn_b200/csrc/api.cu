@@ -1,0 +1,481 @@
+// api.cu -- the C ABI of libhpmn_b200.so (include/hpmn_b200.h) and the step orchestration.
+// Everything the reference does inside one `sess.run` (/root/reference/code/hpmn.py:336,365,482,511) --
+// minus the Adam apply, which is hpmn_clip_adam -- is enqueued here on the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+using namespace hpmn;
+
+struct hpmn_ctx {
+  int device;
+  int sms;
+  int64_t launches;
+  char err[512];
+  float* scratch;   // 256 B of device memory (sink for the id-range flag of the granular gather)
+  // profiling (CUDA events on the caller's stream around each kernel family)
+  bool profile;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used;
+  struct Span { int fam; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double ms[HPMN_K_COUNT];
+  int64_t calls[HPMN_K_COUNT];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(hpmn_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_create_err;
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, HPMN_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int check_launch(hpmn_ctx* ctx, const char* where) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, HPMN_ECUDA, "%s: kernel launch failed: %s", where, cudaGetErrorString(e));
+  }
+  return HPMN_OK;
+}
+
+// ---- profiling helpers ----------------------------------------------------------------------
+static void prof_flush(hpmn_ctx* ctx) {
+  for (auto& s : ctx->spans) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      ctx->ms[s.fam] += ms;
+      ctx->calls[s.fam] += 1;
+    }
+  }
+  ctx->spans.clear();
+  ctx->pool_used = 0;
+}
+
+struct Bracket {          // RAII: records an event pair around a kernel family when profiling is on
+  hpmn_ctx* ctx; cudaStream_t st; int fam; cudaEvent_t a, b; bool on;
+  Bracket(hpmn_ctx* c, cudaStream_t s, int f) : ctx(c), st(s), fam(f), on(false) {
+    if (!c->profile) return;
+    if (c->pool_used + 2 > c->pool.size()) prof_flush(c);
+    a = c->pool[c->pool_used++]; b = c->pool[c->pool_used++];
+    cudaEventRecord(a, st);
+    on = true;
+  }
+  ~Bracket() {
+    if (!on) return;
+    cudaEventRecord(b, st);
+    ctx->spans.push_back({fam, a, b});
+  }
+};
+
+static const char* kFamilyNames[HPMN_K_COUNT] = {"gather_fwd", "inproj_gemm", "rec_fwd", "attn_fwd", "head_fwd", "head_bwd",
+                                                 "attn_bwd", "rec_bwd", "dx_gemm", "gru_wgrad", "scatter_add", "misc"};
+
+// ---- shared plumbing ------------------------------------------------------------------------
+struct Plan {
+  Dims d; ParamLayout pl; PackLayout pk; WsLayout wl;
+  char* ws;
+  float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+  AttWs att() const { return AttWs{f(wl.att_q), f(wl.att_dq), f(wl.att_w), f(wl.att_ds), f(wl.att_inp), f(wl.att_z1),
+                                   f(wl.att_dz1), f(wl.att_z2), f(wl.att_dz2)}; }
+  HeadWs head() const { return HeadWs{f(wl.head_bn), f(wl.head_dbn), f(wl.head_dgt), f(wl.head_a1), f(wl.head_act1),
+                                      f(wl.head_dl1), f(wl.head_a2), f(wl.head_act2), f(wl.head_dl2), f(wl.head_dlogit)}; }
+};
+
+static int make_plan(hpmn_ctx* ctx, const hpmn_shape* s, void* workspace, Plan& p) {
+  if (!ctx) return HPMN_EINVAL;
+  p.d = make_dims(s);
+  if (!p.d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape (need E%%4==0, H<=32, L<=16, hops<=8, steps divisible by periods)");
+  if (p.d.D > 64) return fail(ctx, HPMN_EINVAL, "F*E = %d > 64 is not supported by this build", p.d.D);
+  p.pl = make_param_layout(p.d);
+  p.pk = make_pack_layout(p.d);
+  p.wl = make_ws_layout(p.d);
+  p.ws = static_cast<char*>(workspace);
+  if (!workspace) return fail(ctx, HPMN_EINVAL, "workspace is NULL");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ctx, HPMN_EINVAL, "workspace must be 256-byte aligned");
+  cudaSetDevice(ctx->device);
+  return HPMN_OK;
+}
+
+static hpmn_hyper default_hyper() { hpmn_hyper h; memset(&h, 0, sizeof(h)); h.memory_reg = 1e-5f; h.keep_prob = 1.f; return h; }
+
+// memory forward: pack + per layer (projection GEMM, recurrence)
+static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory,
+                           cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  float* pw = p.f(p.wl.pw);
+  { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
+  for (int k = 0; k < d.L; ++k) {
+    const float* A = k == 0 ? x : p.f(p.wl.hs[k - 1]) + (int64_t)(d.P[k - 1] - 1) * HP;
+    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * HP;
+    { Bracket b(ctx, st, HPMN_K_INPROJ);
+      launch_gemm_nn(L, A, lda, pw + p.pk.Wx[k], pw + p.pk.bx[k], p.f(p.wl.proj[k]), (int64_t)d.B * d.S[k], G3, d.DinP[k], st); }
+    { Bracket b(ctx, st, HPMN_K_REC_FWD);
+      launch_rec_fwd(L, d, k, p.f(p.wl.proj[k]), pw + p.pk.Wh[k], p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), memory, st); }
+  }
+}
+
+// memory backward: top layer first; da overwrites the projections
+static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const float* dmemory, float* dx0, float* grads,
+                           cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  float* pw = p.f(p.wl.pw);
+  for (int k = d.L - 1; k >= 0; --k) {
+    float* da = p.f(p.wl.proj[k]);
+    const float* dx_up = k < d.L - 1 ? p.f(p.wl.dxk[k + 1]) : nullptr;
+    { Bracket b(ctx, st, HPMN_K_REC_BWD);
+      launch_rec_bwd(L, d, k, p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), pw + p.pk.WhT[k], dmemory, dx_up, da, st); }
+    float* dxk = k == 0 ? dx0 : p.f(p.wl.dxk[k]);
+    { Bracket b(ctx, st, HPMN_K_DX);
+      launch_gemm_nn(L, da, G3, pw + p.pk.WxT[k], nullptr, dxk, (int64_t)d.B * d.S[k], d.DinP[k], G3, st); }
+    const float* A = k == 0 ? x : p.f(p.wl.hs[k - 1]) + (int64_t)(d.P[k - 1] - 1) * HP;
+    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * HP;
+    { Bracket b(ctx, st, HPMN_K_WGRAD);
+      launch_gru_wgrad(L, d, k, A, lda, p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
+                       grads + p.pl.Wc[k], grads + p.pl.bc[k], st); }
+  }
+}
+
+// ---- sum of squares (only for l2_reg != 0) ---------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, int64_t n, float scale, float* out) {
+  float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fmaf(v[i], v[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+}
+
+// =============================================================================================
+extern "C" {
+
+int hpmn_abi_version(void) { return HPMN_ABI_VERSION; }
+
+int hpmn_create(hpmn_ctx** out, int device) {
+  hpmn_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, HPMN_EINVAL, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, HPMN_ECUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, HPMN_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, HPMN_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, HPMN_EARCH, "device %d is sm_%d%d; libhpmn_b200 is built for sm_100a only", device, prop.major, prop.minor);
+  ctx = new (std::nothrow) hpmn_ctx();
+  if (!ctx) return fail(nullptr, HPMN_ENOMEM, "out of host memory");
+  ctx->device = device; ctx->sms = prop.multiProcessorCount; ctx->launches = 0; ctx->err[0] = 0;
+  ctx->profile = false; ctx->pool_used = 0;
+  memset(ctx->ms, 0, sizeof(ctx->ms)); memset(ctx->calls, 0, sizeof(ctx->calls));
+  cudaSetDevice(device);
+  e = cudaMalloc(&ctx->scratch, 256);
+  if (e != cudaSuccess) { delete ctx; return fail(nullptr, HPMN_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  *out = ctx;
+  return HPMN_OK;
+}
+
+void hpmn_destroy(hpmn_ctx* ctx) {
+  if (!ctx) return;
+  for (auto e : ctx->pool) cudaEventDestroy(e);
+  cudaFree(ctx->scratch);
+  delete ctx;
+}
+
+const char* hpmn_last_error(hpmn_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+int64_t hpmn_launch_count(hpmn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hpmn_param_tensors(const hpmn_shape* s) {
+  Dims d = make_dims(s);
+  if (!d.ok) return HPMN_EINVAL;
+  return make_param_layout(d).ntensors;
+}
+int64_t hpmn_param_count(const hpmn_shape* s) {
+  Dims d = make_dims(s);
+  if (!d.ok) return HPMN_EINVAL;
+  return make_param_layout(d).total;
+}
+int hpmn_param_offsets(const hpmn_shape* s, int64_t* offsets, int64_t* sizes, int n) {
+  Dims d = make_dims(s);
+  if (!d.ok || !offsets || !sizes) return HPMN_EINVAL;
+  int i = 0;
+  ParamLayout pl = make_param_layout(d, [&](int64_t off, int64_t sz) { if (i < n) { offsets[i] = off; sizes[i] = sz; } ++i; });
+  return pl.ntensors <= n ? pl.ntensors : HPMN_EINVAL;
+}
+size_t hpmn_workspace_bytes(const hpmn_shape* s, int for_bwd) {
+  (void)for_bwd;   // forward keeps the same activations (eval and train share one layout)
+  Dims d = make_dims(s);
+  if (!d.ok) return 0;
+  return make_ws_layout(d).total;
+}
+
+const char* hpmn_kernel_family_name(int f) { return f >= 0 && f < HPMN_K_COUNT ? kFamilyNames[f] : "?"; }
+
+int hpmn_profile_enable(hpmn_ctx* ctx, int on) {
+  if (!ctx) return HPMN_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (on && ctx->pool.empty()) {
+    ctx->pool.resize(2048);
+    for (auto& e : ctx->pool) CK(cudaEventCreate(&e));
+  }
+  if (!on) prof_flush(ctx);
+  ctx->profile = on != 0;
+  return HPMN_OK;
+}
+int hpmn_profile_read(hpmn_ctx* ctx, float* ms, int64_t* calls) {
+  if (!ctx || !ms || !calls) return HPMN_EINVAL;
+  prof_flush(ctx);
+  for (int i = 0; i < HPMN_K_COUNT; ++i) { ms[i] = (float)ctx->ms[i]; calls[i] = ctx->calls[i]; ctx->ms[i] = 0; ctx->calls[i] = 0; }
+  return HPMN_OK;
+}
+
+// ---- K1 / K5 ----------------------------------------------------------------------------------
+int hpmn_gather_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const int32_t* ids, const float* table, float* x, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  Dims d = make_dims(s);
+  if (!d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape");
+  if (!ids || !table || !x) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  cudaSetDevice(ctx->device);
+  Launch L{&ctx->launches, ctx->sms};
+  // out-of-range ids cannot be reported without a sync here: rows are zero-filled (see hpmn_step_host)
+  launch_gather_fwd(L, d, s->mask_id0 != 0, s->front_pad, s->V, ids, table, x, ctx->scratch, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_gather_fwd");
+}
+
+int hpmn_gather_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const int32_t* ids, const float* dx, const float* dlast,
+                    float* dtable, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  Dims d = make_dims(s);
+  if (!d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape");
+  if (!ids || !dx || !dtable) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  cudaSetDevice(ctx->device);
+  Launch L{&ctx->launches, ctx->sms};
+  launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids, dx, dlast, dtable, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_gather_bwd");
+}
+
+// ---- K2 / K4 ----------------------------------------------------------------------------------
+int hpmn_memory_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const float* params, float* memory,
+                    void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!x || !params || !memory) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  run_memory_fwd(ctx, p, x, params, memory, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_memory_fwd");
+}
+
+int hpmn_memory_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const float* params, const float* dmemory,
+                    float* dx, float* grads, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!x || !params || !dmemory || !dx || !grads) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Launch L{&ctx->launches, ctx->sms};
+  launch_pack(L, p.d, p.pl, p.pk, params, p.f(p.wl.pw), st);
+  run_memory_bwd(ctx, p, x, dmemory, dx, grads, st);
+  return check_launch(ctx, "hpmn_memory_bwd");
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------
+int hpmn_attn_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* memory, const float* x, const float* params,
+                  float* repre, float* w_hop0, float* scalars, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!memory || !x || !params || !repre || !w_hop0 || !scalars) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  launch_attn_fwd(L, p.d, p.pl, s->last_offset, memory, x, params, repre, w_hop0, scalars, p.att(), (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_attn_fwd");
+}
+
+int hpmn_attn_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const float* memory, const float* x,
+                  const float* params, const float* drepre, float* dmemory, float* dlast, float* grads, void* workspace,
+                  void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!hy || !memory || !x || !params || !drepre || !dmemory || !dlast || !grads) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  AtbBatch batch; batch.n = 0; batch.blocks = 0;
+  launch_attn_bwd(L, p.d, p.pl, s->last_offset, hy->memory_reg, memory, x, params, drepre, dmemory, dlast, grads, p.att(),
+                  batch, (cudaStream_t)stream);
+  launch_atb_batch(L, batch, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_attn_bwd");
+}
+
+// ---- head -------------------------------------------------------------------------------------
+int hpmn_head_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const float* repre, const int32_t* labels,
+                  const float* params, float* pred, float* logit, float* scalars, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!hy || !repre || !labels || !params || !pred || !logit || !scalars) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  // pred / logit are staged in the workspace (hpmn_head_bwd reads pred from there), then copied out
+  launch_head_fwd(L, p.d, p.pl, *hy, repre, labels, params, p.f(p.wl.pred), p.f(p.wl.logit), scalars, p.head(), (cudaStream_t)stream);
+  CK(cudaMemcpyAsync(pred, p.f(p.wl.pred), (size_t)p.d.B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CK(cudaMemcpyAsync(logit, p.f(p.wl.logit), (size_t)p.d.B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return check_launch(ctx, "hpmn_head_fwd");
+}
+
+int hpmn_head_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const float* repre, const int32_t* labels,
+                  const float* params, float* drepre, float* grads, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!hy || !repre || !labels || !params || !drepre || !grads) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  AtbBatch batch; batch.n = 0; batch.blocks = 0;
+  // pred of the preceding hpmn_head_fwd on this workspace
+  launch_head_bwd(L, p.d, p.pl, *hy, repre, labels, params, p.f(p.wl.pred), drepre, grads, p.head(), batch, (cudaStream_t)stream);
+  launch_atb_batch(L, batch, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_head_bwd");
+}
+
+// ---- whole path -------------------------------------------------------------------------------
+static int run_forward(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hpmn_hyper& hy, const int32_t* ids,
+                       const int32_t* labels, const float* params, const float* table, const hpmn_outputs* out,
+                       cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  float* x = p.f(p.wl.x);
+  float* memory = p.f(p.wl.memory);
+  float* scalars = out->scalars;
+  float* pred = p.f(p.wl.pred);             // always staged in the workspace (head_bwd reads it)
+  float* logit = p.f(p.wl.logit);
+  float* w0 = out->w_hop0 ? out->w_hop0 : p.f(p.wl.w_hop0);
+  CK(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
+  { Bracket b(ctx, st, HPMN_K_GATHER);
+    launch_gather_fwd(L, d, s->mask_id0 != 0, s->front_pad, s->V, ids, table, x, scalars + HPMN_S_IDERR, st); }
+  run_memory_fwd(ctx, p, x, params, memory, st);
+  { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
+    launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), w0, scalars, p.att(), st); }
+  { Bracket b(ctx, st, HPMN_K_HEAD_FWD);
+    launch_head_fwd(L, d, p.pl, hy, p.f(p.wl.repre), labels, params, pred, logit, scalars, p.head(), st); }
+  { Bracket b(ctx, st, HPMN_K_MISC);
+    launch_finish_scalars(L, scalars, hy.memory_reg, st);
+    if (hy.l2_reg != 0.f) {
+      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(params, p.pl.total, 0.5f * hy.l2_reg, scalars + HPMN_S_LOSS);
+      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(table, s->V * (int64_t)d.E, 0.5f * hy.l2_reg, scalars + HPMN_S_LOSS);
+      ctx->launches += 2;
+    }
+    if (out->pred) CK(cudaMemcpyAsync(out->pred, pred, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->logit) CK(cudaMemcpyAsync(out->logit, logit, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->memory) CK(cudaMemcpyAsync(out->memory, memory, (size_t)d.B * d.L * d.H * sizeof(float), cudaMemcpyDeviceToDevice, st)); }
+  return HPMN_OK;
+}
+
+static int run_backward(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hpmn_hyper& hy, const int32_t* ids,
+                        const int32_t* labels, const float* params, const float* table, float* grads, float* dtable,
+                        int zero_dtable, cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  float* x = p.f(p.wl.x);
+  { Bracket b(ctx, st, HPMN_K_MISC);
+    CK(cudaMemsetAsync(grads, 0, (size_t)p.pl.total * sizeof(float), st));
+    if (zero_dtable) CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st)); }
+  AtbBatch batch; batch.n = 0; batch.blocks = 0;
+  { Bracket b(ctx, st, HPMN_K_HEAD_BWD);
+    launch_head_bwd(L, d, p.pl, hy, p.f(p.wl.repre), labels, params, p.f(p.wl.pred), p.f(p.wl.drepre), grads, p.head(), batch, st); }
+  { Bracket b(ctx, st, HPMN_K_ATTN_BWD);
+    launch_attn_bwd(L, d, p.pl, s->last_offset, hy.memory_reg, p.f(p.wl.memory), x, params, p.f(p.wl.drepre),
+                    p.f(p.wl.dmemory), p.f(p.wl.dlast), grads, p.att(), batch, st);
+    launch_atb_batch(L, batch, st); }
+  run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), p.f(p.wl.dxk[0]), grads, st);
+  { Bracket b(ctx, st, HPMN_K_SCATTER);
+    launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids, p.f(p.wl.dxk[0]), p.f(p.wl.dlast),
+                      dtable, st); }
+  if (hy.l2_reg != 0.f) {   // l2_reg * tf.nn.l2_loss(v) over every trainable, code/hpmn.py:204-205
+    Bracket b(ctx, st, HPMN_K_MISC);
+    launch_axpy(L, grads, params, hy.l2_reg, p.pl.total, st);
+    launch_axpy(L, dtable, table, hy.l2_reg, s->V * (int64_t)d.E, st);
+  }
+  return HPMN_OK;
+}
+
+int hpmn_forward(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids, const int32_t* labels,
+                 const float* params, const float* table, const hpmn_outputs* out, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!ids || !labels || !params || !table || !out || !out->scalars) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  hpmn_hyper h = hy ? *hy : default_hyper();
+  rc = run_forward(ctx, p, s, h, ids, labels, params, table, out, (cudaStream_t)stream);
+  if (rc) return rc;
+  return check_launch(ctx, "hpmn_forward");
+}
+
+int hpmn_forward_backward(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids,
+                          const int32_t* labels, const float* params, const float* table, float* grads, float* dtable,
+                          int zero_dtable, const hpmn_outputs* out, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!ids || !labels || !params || !table || !grads || !dtable || !out || !out->scalars)
+    return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  hpmn_hyper h = hy ? *hy : default_hyper();
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_forward(ctx, p, s, h, ids, labels, params, table, out, st);
+  if (rc) return rc;
+  rc = run_backward(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, st);
+  if (rc) return rc;
+  return check_launch(ctx, "hpmn_forward_backward");
+}
+
+int hpmn_step_host(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids_host,
+                   const int32_t* labels_host, const float* params, const float* table, float* grads, float* dtable,
+                   int zero_dtable, int with_backward, const hpmn_outputs* oh, void* workspace, void* stream) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!ids_host || !labels_host || !params || !table || !oh || !oh->scalars) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  if (with_backward && (!grads || !dtable)) return fail(ctx, HPMN_EINVAL, "NULL gradient buffer");
+  hpmn_hyper h = hy ? *hy : default_hyper();
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims& d = p.d;
+  int32_t* ids = reinterpret_cast<int32_t*>(p.ws + p.wl.ids);
+  int32_t* labels = reinterpret_cast<int32_t*>(p.ws + p.wl.labels);
+  CK(cudaMemcpyAsync(ids, ids_host, (size_t)d.B * d.T * d.F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(labels, labels_host, (size_t)d.B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  hpmn_outputs od; memset(&od, 0, sizeof(od));
+  od.scalars = p.f(p.wl.scalars);
+  od.w_hop0 = p.f(p.wl.w_hop0);
+  rc = run_forward(ctx, p, s, h, ids, labels, params, table, &od, st);
+  if (rc) return rc;
+  if (with_backward) {
+    rc = run_backward(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, st);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(oh->scalars, od.scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (oh->pred) CK(cudaMemcpyAsync(oh->pred, p.f(p.wl.pred), (size_t)d.B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (oh->logit) CK(cudaMemcpyAsync(oh->logit, p.f(p.wl.logit), (size_t)d.B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (oh->w_hop0) CK(cudaMemcpyAsync(oh->w_hop0, od.w_hop0, (size_t)d.B * d.L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (oh->memory) CK(cudaMemcpyAsync(oh->memory, p.f(p.wl.memory), (size_t)d.B * d.L * d.H * sizeof(float), cudaMemcpyDeviceToHost, st));
+  rc = check_launch(ctx, "hpmn_step_host");
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  if (oh->scalars[HPMN_S_IDERR] != 0.f)   // TF's GatherV2 raises InvalidArgumentError on CPU
+    return fail(ctx, HPMN_EINVAL, "an id is outside [0, feature_size=%lld)", (long long)s->V);
+  return HPMN_OK;
+}
+
+int hpmn_clip_adam(hpmn_ctx* ctx, float* var, const float* grad, float* m, float* v, int64_t n, int64_t t, float lr,
+                   float beta1, float beta2, float eps, float clip, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  if (!var || !grad || !m || !v || n < 0 || t < 1) return fail(ctx, HPMN_EINVAL, "bad argument");
+  cudaSetDevice(ctx->device);
+  Launch L{&ctx->launches, ctx->sms};
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+  launch_clip_adam(L, var, grad, m, v, n, (float)lr_t, beta1, beta2, eps, clip, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_clip_adam");
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// common.cuh -- shared host/device helpers for libhpmn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hpmn_b200.h"
+
+namespace hpmn {
+
+constexpr int HP = 32;        // hidden width padded to one warp (this build: H <= 32)
+constexpr int G3 = 3 * HP;    // r | u | c columns of a packed gate row
+constexpr int ATT1 = 80;      // code/hpmn.py:137
+constexpr int ATT2 = 40;      // code/hpmn.py:138
+constexpr int FC1 = 200;      // code/hpmn.py:191
+constexpr int FC2 = 80;       // code/hpmn.py:193
+constexpr float BN_EPS = 1e-3f;
+constexpr float LOGLOSS_EPS = 1e-7f;
+
+struct hpmn_ctx_impl;
+
+// ---------------------------------------------------------------------------------------------
+// derived dimensions
+// ---------------------------------------------------------------------------------------------
+struct Dims {
+  int B, T, Tpad, F, E, D, H, L, hops, R;   // R = H + D (head input)
+  int S[HPMN_MAX_LAYERS];                     // steps of layer k
+  int Din[HPMN_MAX_LAYERS];                   // real input width of layer k
+  int DinP[HPMN_MAX_LAYERS];                  // padded input width (D for k=0, HP above)
+  int P[HPMN_MAX_LAYERS];                     // period of layer k (k < L-1), 1 for the top layer
+  int64_t rows_total;                         // sum_k B*S_k
+  bool ok;
+};
+
+inline Dims make_dims(const hpmn_shape* s) {
+  Dims d; memset(&d, 0, sizeof(d));
+  d.ok = false;
+  if (!s) return d;
+  if (s->B <= 0 || s->T <= 0 || s->F <= 0 || s->E <= 0 || (s->E & 3) || s->H <= 0 || s->H > HP) return d;
+  if (s->L <= 0 || s->L > HPMN_MAX_LAYERS || s->hops <= 0 || s->hops > HPMN_MAX_HOPS) return d;
+  if (s->front_pad < 0 || s->last_offset < 1 || s->V <= 0) return d;
+  d.B = s->B; d.T = s->T; d.Tpad = s->T + s->front_pad; d.F = s->F; d.E = s->E; d.D = s->F * s->E;
+  d.H = s->H; d.L = s->L; d.hops = s->hops; d.R = d.H + d.D;
+  if (s->last_offset > d.Tpad) return d;
+  if (d.D > 256) return d;
+  int steps = d.Tpad;
+  for (int k = 0; k < d.L; ++k) {
+    d.S[k] = steps;
+    d.Din[k] = k == 0 ? d.D : d.H;
+    d.DinP[k] = k == 0 ? d.D : HP;
+    d.rows_total += (int64_t)d.B * steps;
+    if (k < d.L - 1) {
+      int p = s->periods[k];
+      if (p <= 0 || steps % p) return d;
+      d.P[k] = p;
+      steps /= p;
+    } else {
+      d.P[k] = 1;
+    }
+  }
+  d.ok = true;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat parameter layout (see include/hpmn_b200.h)
+// ---------------------------------------------------------------------------------------------
+struct ParamLayout {
+  int64_t Wg[HPMN_MAX_LAYERS], bg[HPMN_MAX_LAYERS], Wc[HPMN_MAX_LAYERS], bc[HPMN_MAX_LAYERS];
+  int64_t Wq, bq, Hmap;
+  int64_t A1[HPMN_MAX_HOPS], a1[HPMN_MAX_HOPS], A2[HPMN_MAX_HOPS], a2[HPMN_MAX_HOPS], A3[HPMN_MAX_HOPS], a3[HPMN_MAX_HOPS];
+  int64_t gamma, beta, F1, f1, F2, f2, F3, f3;
+  int64_t total;
+  int ntensors;
+};
+
+inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+// visit(offset, size) is called once per tensor in canonical order
+template <class Visit>
+inline ParamLayout make_param_layout(const Dims& d, Visit visit) {
+  ParamLayout p; memset(&p, 0, sizeof(p));
+  int64_t off = 0; int n = 0;
+  auto take = [&](int64_t sz) { int64_t o = off; visit(o, sz); off = align4(off + sz); ++n; return o; };
+  for (int k = 0; k < d.L; ++k) {
+    int in = d.Din[k] + d.H;
+    p.Wg[k] = take((int64_t)in * 2 * d.H); p.bg[k] = take(2 * d.H);
+    p.Wc[k] = take((int64_t)in * d.H);     p.bc[k] = take(d.H);
+  }
+  p.Wq = take((int64_t)d.D * d.H); p.bq = take(d.H); p.Hmap = take((int64_t)d.H * d.H);
+  for (int h = 0; h < d.hops; ++h) {
+    p.A1[h] = take((int64_t)4 * d.H * ATT1); p.a1[h] = take(ATT1);
+    p.A2[h] = take((int64_t)ATT1 * ATT2);    p.a2[h] = take(ATT2);
+    p.A3[h] = take(ATT2);                    p.a3[h] = take(1);
+  }
+  p.gamma = take(d.R); p.beta = take(d.R);
+  p.F1 = take((int64_t)d.R * FC1); p.f1 = take(FC1);
+  p.F2 = take((int64_t)FC1 * FC2); p.f2 = take(FC2);
+  p.F3 = take(FC2); p.f3 = take(1);
+  p.total = off; p.ntensors = n;
+  return p;
+}
+inline ParamLayout make_param_layout(const Dims& d) { return make_param_layout(d, [](int64_t, int64_t) {}); }
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (byte offsets, 256-B aligned)
+// ---------------------------------------------------------------------------------------------
+struct WsLayout {
+  size_t ids, labels;                 // device staging for the *_host entry points
+  size_t x;                           // [B,Tpad,D]
+  size_t pw;                          // packed weights (see PackLayout), rebuilt every call
+  size_t proj[HPMN_MAX_LAYERS];       // [B,S_k,3,HP]  input projections; reused as da in bwd
+  size_t hs[HPMN_MAX_LAYERS];         // [B,S_k,HP]    hidden outputs
+  size_t gates[HPMN_MAX_LAYERS];      // [B,S_k,3,HP]  r,u,c
+  size_t dxk[HPMN_MAX_LAYERS];        // k>=1: [B,S_k,HP] gradient wrt layer input; k=0: [B,Tpad,D]
+  size_t memory, dmemory;             // [B,L,H]
+  size_t att_q, att_dq;               // [hops+1][B,H]  query before each hop (+ final) and its gradient
+  size_t att_w, att_ds;               // [hops][B,L]    softmax weights, d score
+  size_t att_inp;                     // [hops][B,L,4H] concat [q, m, q-m, q*m]
+  size_t att_z1, att_dz1;             // [hops][B,L,80]
+  size_t att_z2, att_dz2;             // [hops][B,L,40]
+  size_t repre, drepre;               // [B,R]
+  size_t dlast;                       // [B,D]
+  size_t head_bn, head_dbn, head_dgt; // [B,R]  bn output, its gradient, gradient * x_hat (for gamma)
+  size_t head_a1, head_act1, head_dl1;// [B,200] pre-activation, post-dropout activation, delta
+  size_t head_a2, head_act2, head_dl2;// [B,80]
+  size_t head_dlogit;                 // [B]
+  size_t pred, logit, w_hop0, scalars;// outputs staging
+  size_t total;
+};
+
+struct PackLayout {                    // float offsets inside the packed-weights block
+  int64_t Wx[HPMN_MAX_LAYERS];        // [DinP, 96]  input weights, cols g*32+j
+  int64_t bx[HPMN_MAX_LAYERS];        // [96]
+  int64_t Wh[HPMN_MAX_LAYERS];        // [3][32 i][32 j] recurrent weights (fwd, lane j coalesced)
+  int64_t WhT[HPMN_MAX_LAYERS];       // [3][32 j][32 i] transposed (bwd, lane i coalesced)
+  int64_t WxT[HPMN_MAX_LAYERS];       // [96, DinP]
+  int64_t total;
+};
+
+inline PackLayout make_pack_layout(const Dims& d) {
+  PackLayout p; memset(&p, 0, sizeof(p));
+  int64_t off = 0;
+  for (int k = 0; k < d.L; ++k) {
+    p.Wx[k] = off;  off += (int64_t)d.DinP[k] * G3;
+    p.bx[k] = off;  off += G3;
+    p.Wh[k] = off;  off += 3 * HP * HP;
+    p.WhT[k] = off; off += 3 * HP * HP;
+    p.WxT[k] = off; off += (int64_t)G3 * d.DinP[k];
+  }
+  p.total = off;
+  return p;
+}
+
+inline WsLayout make_ws_layout(const Dims& d) {
+  WsLayout w; memset(&w, 0, sizeof(w));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t f = sizeof(float);
+  w.ids = take((size_t)d.B * d.T * d.F * sizeof(int32_t));
+  w.labels = take((size_t)d.B * sizeof(int32_t));
+  w.x = take((size_t)d.B * d.Tpad * d.D * f);
+  w.pw = take((size_t)make_pack_layout(d).total * f);
+  for (int k = 0; k < d.L; ++k) {
+    size_t rows = (size_t)d.B * d.S[k];
+    w.proj[k] = take(rows * G3 * f);
+    w.hs[k] = take(rows * HP * f);
+    w.gates[k] = take(rows * G3 * f);
+    w.dxk[k] = take(rows * (k == 0 ? d.D : HP) * f);
+  }
+  w.memory = take((size_t)d.B * d.L * d.H * f);
+  w.dmemory = take((size_t)d.B * d.L * d.H * f);
+  w.att_q = take((size_t)(d.hops + 1) * d.B * d.H * f);
+  w.att_dq = take((size_t)(d.hops + 1) * d.B * d.H * f);
+  w.att_w = take((size_t)d.hops * d.B * d.L * f);
+  w.att_ds = take((size_t)d.hops * d.B * d.L * f);
+  w.att_inp = take((size_t)d.hops * d.B * d.L * 4 * d.H * f);
+  w.att_z1 = take((size_t)d.hops * d.B * d.L * ATT1 * f);
+  w.att_dz1 = take((size_t)d.hops * d.B * d.L * ATT1 * f);
+  w.att_z2 = take((size_t)d.hops * d.B * d.L * ATT2 * f);
+  w.att_dz2 = take((size_t)d.hops * d.B * d.L * ATT2 * f);
+  w.repre = take((size_t)d.B * d.R * f);
+  w.drepre = take((size_t)d.B * d.R * f);
+  w.dlast = take((size_t)d.B * d.D * f);
+  w.head_bn = take((size_t)d.B * d.R * f);
+  w.head_dbn = take((size_t)d.B * d.R * f);
+  w.head_dgt = take((size_t)d.B * d.R * f);
+  w.head_a1 = take((size_t)d.B * FC1 * f);
+  w.head_act1 = take((size_t)d.B * FC1 * f);
+  w.head_dl1 = take((size_t)d.B * FC1 * f);
+  w.head_a2 = take((size_t)d.B * FC2 * f);
+  w.head_act2 = take((size_t)d.B * FC2 * f);
+  w.head_dl2 = take((size_t)d.B * FC2 * f);
+  w.head_dlogit = take((size_t)d.B * f);
+  w.pred = take((size_t)d.B * f);
+  w.logit = take((size_t)d.B * f);
+  w.w_hop0 = take((size_t)d.B * d.L * f);
+  w.scalars = take(4 * f);
+  w.total = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// exp via ex2.approx (<= 2 ulp) -- error ~1e-7 relative, far inside the 1e-4 parity budget
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) {
+  // 1 - 2/(1+e^{2x}); saturates cleanly for |x| large (e^{2x} -> inf gives 1, -> 0 gives -1)
+  float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (defined in the .cu files; all asynchronous on `st`)
+// ---------------------------------------------------------------------------------------------
+struct Launch {   // launch bookkeeping shared with the ctx
+  int64_t* counter;
+  int sms;
+};
+
+void launch_gather_fwd(const Launch&, const Dims&, bool mask_id0, int front_pad, int64_t V, const int32_t* ids,
+                       const float* table, float* x, float* iderr, cudaStream_t st);
+void launch_gather_bwd(const Launch&, const Dims&, bool mask_id0, int front_pad, int last_offset, int64_t V,
+                       const int32_t* ids, const float* dx, const float* dlast, float* dtable, cudaStream_t st);
+
+void launch_pack(const Launch&, const Dims&, const ParamLayout&, const PackLayout&, const float* params, float* pw,
+                 cudaStream_t st);
+// C[M,N] = A[M,K](row stride lda) * W[K,N] (+ bias[N]); N, K multiples of 4
+void launch_gemm_nn(const Launch&, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
+                    int N, int K, cudaStream_t st);
+// batched C[I,N](ldc) += sum_m A[m,I](lda) * Bm[m,N](ldb) with atomic accumulation; A == nullptr -> ones
+struct AtbProb {
+  const float* A; const float* Bm; float* C;
+  int64_t lda, ldb, ldc, M, rows_per_split;
+  int I, N, block_begin, pad_;
+};
+constexpr int ATB_MAX = 40;
+struct AtbBatch { int n; int blocks; AtbProb p[ATB_MAX]; };
+void atb_add(AtbBatch& batch, int sms, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
+             int64_t M, int I, int N);
+void launch_atb_batch(const Launch&, const AtbBatch& batch, cudaStream_t st);
+
+void launch_rec_fwd(const Launch&, const Dims&, int k, const float* proj, const float* Wh, float* hs, float* gates,
+                    float* memory, cudaStream_t st);
+void launch_rec_bwd(const Launch&, const Dims&, int k, const float* hs, const float* gates, const float* WhT,
+                    const float* dmemory, const float* dx_up, float* da, cudaStream_t st);
+void launch_gru_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* hs,
+                      const float* gates, const float* da, float* dWg, float* dbg, float* dWc, float* dbc,
+                      cudaStream_t st);
+
+// resolved workspace pointers handed to the attention / head kernels
+struct AttWs { float *q, *dq, *w, *ds, *inp, *z1, *dz1, *z2, *dz2; };
+struct HeadWs { float *bn, *dbn, *dgt, *a1, *act1, *dl1, *a2, *act2, *dl2, *dlogit; };
+
+void launch_attn_fwd(const Launch&, const Dims&, const ParamLayout&, int last_offset, const float* memory, const float* x,
+                     const float* params, float* repre, float* w_hop0, float* scalars, const AttWs& ws, cudaStream_t st);
+// per-sample deltas only; weight gradients are queued on `batch` (launch_atb_batch)
+void launch_attn_bwd(const Launch&, const Dims&, const ParamLayout&, int last_offset, float memory_reg, const float* memory,
+                     const float* x, const float* params, const float* drepre, float* dmemory, float* dlast, float* grads,
+                     const AttWs& ws, AtbBatch& batch, cudaStream_t st);
+
+void launch_head_fwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, const float* repre,
+                     const int32_t* labels, const float* params, float* pred, float* logit, float* scalars,
+                     const HeadWs& ws, cudaStream_t st);
+void launch_head_bwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, const float* repre,
+                     const int32_t* labels, const float* params, const float* pred, float* drepre, float* grads,
+                     const HeadWs& ws, AtbBatch& batch, cudaStream_t st);
+
+void launch_clip_adam(const Launch&, float* var, const float* grad, float* m, float* v, int64_t n, float lr_t, float b1,
+                      float b2, float eps, float clip, cudaStream_t st);
+void launch_axpy(const Launch&, float* y, const float* x, float a, int64_t n, cudaStream_t st);
+void launch_finish_scalars(const Launch&, float* scalars, float memory_reg, cudaStream_t st);
+
+// dropout keep-mask shared by head fwd/bwd (counter-based hash; deterministic in seed, sample, unit)
+#ifdef __CUDACC__
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t layer, uint32_t b, uint32_t unit, float keep_prob) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)layer * 0x100000000ull + ((uint64_t)b << 10) + unit + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);   // 24 bits -> [0,1)
+  return u < keep_prob;
+}
+#endif
+
+}  // namespace hpmn

@@ -1,0 +1,194 @@
+"""HpmnEngine: owns the device buffers (PyTorch is only the allocator / stream / NCCL plumbing) and calls
+the C ABI of libhpmn_b200.so.  One engine per process / GPU.  It plays the role of the TF session the
+reference builds in /root/reference/code/hpmn.py:57-62,80-89: `forward` is the eval fetch of
+hpmn.py:365-367 / 511-513, `forward_backward` is compute_gradients of hpmn.py:211, `apply_gradients`
+is the clip + Adam of hpmn.py:212-214."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import HpmnShape, param_layout
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class HpmnEngine:
+    def __init__(self, shape: HpmnShape, device: int = 0, memory_reg: float = 1e-5, l2_reg: float = 0.0,
+                 table: Optional[np.ndarray] = None, params: Optional[Dict[str, np.ndarray]] = None,
+                 seed: int = 4321):
+        if not torch.cuda.is_available():
+            raise RuntimeError("hpmn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.shape = shape
+        self.cshape = shape.to_c()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        ctx = C.c_void_p()
+        _lib.check(self.lib.hpmn_create(C.byref(ctx), device))
+        self.ctx = ctx
+        self.layout, self.n_params = param_layout(shape)
+        n_c = self.lib.hpmn_param_count(C.byref(self.cshape))
+        if n_c != self.n_params:
+            raise RuntimeError("parameter layout mismatch: python %d vs C %d" % (self.n_params, n_c))
+        self.memory_reg, self.l2_reg = float(memory_reg), float(l2_reg)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        # trainables + table live in ONE flat buffer [dense params | table] so that the gradient twin is the
+        # single all-reduce message of the data-parallel step and Adam is one sweep
+        self.n_table = shape.V * shape.E
+        self.flat = torch.zeros(self.n_params + self.n_table, **f32)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.params = self.flat[: self.n_params]
+        self.table = self.flat[self.n_params:].view(shape.V, shape.E)
+        self.grads = self.flat_grad[: self.n_params]
+        self.dtable = self.flat_grad[self.n_params:].view(shape.V, shape.E)
+        self.adam_m: Optional[torch.Tensor] = None
+        self.adam_v: Optional[torch.Tensor] = None
+        self.adam_t = 0
+        ws_bytes = self.lib.hpmn_workspace_bytes(C.byref(self.cshape), 1)
+        if ws_bytes == 0:
+            raise ValueError("invalid shape for libhpmn_b200: %r" % (shape,))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        B, L, H = shape.B, shape.L, shape.H
+        self.scalars = torch.zeros(4, **f32)
+        self.pred = torch.zeros(B, **f32)
+        self.logit = torch.zeros(B, **f32)
+        self.w_hop0 = torch.zeros(B, L, **f32)
+        self.memory = torch.zeros(B, L, H, **f32)
+        self._out = _lib.hpmn_outputs(_ptr(self.scalars), _ptr(self.pred), _ptr(self.logit), _ptr(self.w_hop0),
+                                      _ptr(self.memory))
+        # pinned host mirrors for the host-buffer entry point (feed_dict / fetches of hpmn.py:474-482)
+        self.h_ids = torch.empty(B, shape.T, shape.F, dtype=torch.int32).pin_memory()
+        self.h_labels = torch.empty(B, dtype=torch.int32).pin_memory()
+        self.h_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.h_pred = torch.zeros(B, dtype=torch.float32).pin_memory()
+        self.h_logit = torch.zeros(B, dtype=torch.float32).pin_memory()
+        self.h_w_hop0 = torch.zeros(B, L, dtype=torch.float32).pin_memory()
+        self._out_host = _lib.hpmn_outputs(_ptr(self.h_scalars), _ptr(self.h_pred), _ptr(self.h_logit),
+                                           _ptr(self.h_w_hop0), C.c_void_p(0))
+        self.init_parameters(seed)
+        if params is not None:
+            self.load_named(params)
+        if table is not None:
+            self.table.copy_(torch.as_tensor(table, dtype=torch.float32))
+
+    # ------------------------------------------------------------------ parameters
+    def view(self, name: str) -> torch.Tensor:
+        off, shp = self.layout[name]
+        n = int(np.prod(shp))
+        return self.params[off: off + n].view(*shp)
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        off, shp = self.layout[name]
+        n = int(np.prod(shp))
+        return self.grads[off: off + n].view(*shp)
+
+    def init_parameters(self, seed: int = 4321):
+        """TF1.4 defaults: glorot-uniform kernels (get_variable / dense default), GRU gate bias 1.0
+        (util.py:84-86), other biases 0, BN gamma 1 / beta 0."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name, (off, shp) in self.layout.items():
+            v = self.view(name)
+            if name.endswith("kernel") or name.endswith("/map"):
+                lim = float(np.sqrt(6.0 / (shp[0] + shp[1])))
+                v.copy_((torch.rand(*shp, generator=g) * 2 - 1) * lim)
+            elif name.endswith("gates/bias") or name.endswith("gamma"):
+                v.fill_(1.0)
+            else:
+                v.zero_()
+        lim = float(np.sqrt(6.0 / (self.shape.V + self.shape.E)))
+        chunk = 1 << 20
+        for r0 in range(0, self.shape.V, chunk):
+            r1 = min(self.shape.V, r0 + chunk)
+            self.table[r0:r1].copy_((torch.rand(r1 - r0, self.shape.E, generator=g) * 2 - 1) * lim)
+
+    def load_named(self, params: Dict[str, np.ndarray]):
+        for name, arr in params.items():
+            if name in self.layout:
+                self.view(name).copy_(torch.as_tensor(np.asarray(arr), dtype=torch.float32))
+
+    def named_parameters(self) -> Dict[str, np.ndarray]:
+        return {n: self.view(n).detach().cpu().numpy().copy() for n in self.layout}
+
+    def named_grads(self) -> Dict[str, np.ndarray]:
+        return {n: self.grad_view(n).detach().cpu().numpy().copy() for n in self.layout}
+
+    # ------------------------------------------------------------------ calls
+    def _hyper(self, keep_prob: float, seed: int, loss_batch: int) -> "_lib.hpmn_hyper":
+        return _lib.hpmn_hyper(self.memory_reg, self.l2_reg, float(keep_prob), int(seed) & (2 ** 64 - 1), int(loss_batch))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0):
+        """ids [B,T,F] int32 cuda, labels [B] int32 cuda; results land in self.pred / logit / w_hop0 / scalars."""
+        hy = self._hyper(keep_prob, seed, loss_batch)
+        _lib.check(self.lib.hpmn_forward(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(ids), _ptr(labels),
+                                         _ptr(self.params), _ptr(self.table), C.byref(self._out), _ptr(self.workspace),
+                                         self._stream()), self.ctx)
+
+    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0,
+                         loss_batch: int = 0, zero_dtable: bool = True):
+        hy = self._hyper(keep_prob, seed, loss_batch)
+        _lib.check(self.lib.hpmn_forward_backward(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(ids), _ptr(labels),
+                                                  _ptr(self.params), _ptr(self.table), _ptr(self.grads), _ptr(self.dtable),
+                                                  int(zero_dtable), C.byref(self._out), _ptr(self.workspace),
+                                                  self._stream()), self.ctx)
+
+    def step_host(self, ids: np.ndarray, labels: np.ndarray, with_backward: bool = True, keep_prob: float = 1.0,
+                  seed: int = 0, loss_batch: int = 0, zero_dtable: bool = True):
+        """Host buffers in, host results out (pinned staging, H2D + compute + D2H + stream sync inside)."""
+        self.h_ids.numpy()[...] = ids
+        self.h_labels.numpy()[...] = labels
+        return self.step_host_pinned(with_backward, keep_prob, seed, loss_batch, zero_dtable)
+
+    def step_host_pinned(self, with_backward: bool = True, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0,
+                         zero_dtable: bool = True):
+        """Same, with the feed already in self.h_ids / self.h_labels."""
+        hy = self._hyper(keep_prob, seed, loss_batch)
+        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(self.h_ids),
+                                           _ptr(self.h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
+                                           _ptr(self.dtable), int(zero_dtable), int(with_backward),
+                                           C.byref(self._out_host), _ptr(self.workspace), self._stream()), self.ctx)
+        return self.h_scalars.numpy(), self.h_pred.numpy()
+
+    def apply_gradients(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, clip: float = 1.0):
+        """clip_by_value(g,-1,1) + dense Adam over [dense params | table] (hpmn.py:209-214; the clip densifies the
+        embedding gradient in TF1.4, so every table row is touched each step)."""
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+        self.adam_t += 1
+        _lib.check(self.lib.hpmn_clip_adam(self.ctx, _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m),
+                                           _ptr(self.adam_v), self.flat.numel(), self.adam_t, lr, beta1, beta2, eps, clip,
+                                           self._stream()), self.ctx)
+
+    # ------------------------------------------------------------------ measurement
+    def launch_count(self) -> int:
+        return int(self.lib.hpmn_launch_count(self.ctx))
+
+    def profile(self, on: bool):
+        _lib.check(self.lib.hpmn_profile_enable(self.ctx, int(on)), self.ctx)
+
+    def profile_read(self):
+        ms = (C.c_float * len(_lib.K_FAMILIES))()
+        calls = (C.c_int64 * len(_lib.K_FAMILIES))()
+        _lib.check(self.lib.hpmn_profile_read(self.ctx, ms, calls), self.ctx)
+        return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(_lib.K_FAMILIES)}
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.hpmn_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

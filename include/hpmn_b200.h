@@ -1,0 +1,173 @@
+/* hpmn_b200.h -- C ABI of libhpmn_b200.so: the HPMN forward/backward hot path on B200 (sm_100a).
+ *
+ * The reference (alimamarankgroup/HPMN) has no plugin / FFI interface: its hot path is the TF1.4
+ * graph built by code/hpmn.py and executed by `sess.run` (code/hpmn.py:336,365,482,511).  This
+ * header is the boundary a maintainer would bind instead of that `sess.run`: each entry point cites
+ * the reference graph section it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns int (HPMN_OK or a negative HPMN_E*),
+ *     never throws; the message for the last failure is hpmn_last_error(ctx).
+ *   - the CALLER owns every buffer (device memory unless a parameter is called *_host); the library
+ *     borrows it for the call and never allocates device memory after hpmn_create().
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*;
+ *     NULL = legacy default stream); no hidden synchronisation except in the *_host entry points,
+ *     which synchronise the stream before returning (they hand results back in host memory).
+ *   - fp32, row-major, 16-byte aligned; weights keep the TF kernel layout ([D_in+H, 2H] with gate
+ *     columns ordered r then u, code/util.py:88-96) so TF checkpoints map 1:1.
+ *   - a ctx is not thread-safe; distinct ctxs (one per rank / GPU) are independent.
+ *   - there is NO CPU fallback: on a device that is not sm_100 hpmn_create() fails with HPMN_EARCH.
+ */
+#ifndef HPMN_B200_H
+#define HPMN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPMN_ABI_VERSION 1
+#define HPMN_MAX_LAYERS 16
+#define HPMN_MAX_HOPS 8
+
+enum {
+  HPMN_OK = 0,
+  HPMN_EINVAL = -1, /* bad shape / NULL pointer / id out of range */
+  HPMN_EARCH = -2,  /* device is not sm_100 */
+  HPMN_ECUDA = -3,  /* a CUDA call failed; see hpmn_last_error */
+  HPMN_ENOMEM = -4
+};
+
+typedef struct hpmn_ctx hpmn_ctx;
+
+/* Static configuration of one memory side (the `User` scope, code/hpmn.py:436-442 / 287-295). */
+typedef struct hpmn_shape {
+  int32_t B;           /* batch rows held by this rank */
+  int32_t T;           /* id steps per sample as fed (user_maxlen, code/hpmn.py:249) */
+  int32_t F;           /* id features per step (user_dim) */
+  int32_t E;           /* embedding_size (multiple of 4) */
+  int32_t H;           /* hidden_size (<= 32 in this build) */
+  int32_t L;           /* number of GRU layers (user_num_layers) */
+  int32_t hops;        /* self.hop */
+  int32_t front_pad;   /* zero steps prepended: Hpmn_Industry 23 (code/hpmn.py:288-289), Hpmn 0 */
+  int32_t mask_id0;    /* 1: id 0 embeds to zeros (code/hpmn.py:417-423); 0: Hpmn_Industry */
+  int32_t last_offset; /* target step from the end: Hpmn 1 (code/hpmn.py:439), Industry 2 (:292) */
+  int32_t periods[HPMN_MAX_LAYERS]; /* li_layer[k], k < L-1 (code/hpmn.py:122-128) */
+  int64_t V;           /* feature_size: rows of the embedding table */
+} hpmn_shape;
+
+/* Scalars of one step, written to `scalars[4]`: */
+enum { HPMN_S_LOGLOSS = 0, HPMN_S_COVREG = 1, HPMN_S_LOSS = 2, HPMN_S_IDERR = 3 };
+
+/* Loss / regularisation knobs (code/hpmn.py:202-207, 480, 509). */
+typedef struct hpmn_hyper {
+  float memory_reg;     /* weight of the covariance regulariser (memory_loss) */
+  float l2_reg;         /* l2_reg * sum l2_loss(v) over all trainables (0 in every reference config) */
+  float keep_prob;      /* dropout keep probability; 1 = eval */
+  uint64_t dropout_seed;/* counter-based mask seed (TF's RNG stream cannot be matched) */
+  int32_t loss_batch;   /* batch the log-loss mean divides by; 0 = B. Set to the GLOBAL batch when
+                           B is one rank's shard so a SUM all-reduce gives the single-GPU gradient */
+} hpmn_hyper;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int hpmn_abi_version(void);
+int hpmn_create(hpmn_ctx** out, int device);
+void hpmn_destroy(hpmn_ctx* ctx);
+const char* hpmn_last_error(hpmn_ctx* ctx); /* ctx may be NULL: last error of a failed hpmn_create */
+/* number of kernels this ctx has launched since create (bench.py's gpu_launches) */
+int64_t hpmn_launch_count(hpmn_ctx* ctx);
+
+/* ---- layouts (pure host functions, usable without a GPU) ---------------------------------- */
+/* Dense parameters live in ONE flat fp32 buffer (gradients in a twin buffer of the same layout):
+ * for k<L: gates/kernel [Din_k+H,2H], gates/bias [2H], candidate/kernel [Din_k+H,H], candidate/bias [H]
+ * (Din_0 = F*E, Din_k = H); dense/kernel [D,H], dense/bias [H]; map [H,H]; per hop
+ * dense_{3h+1..3h+3}: [4H,80],[80],[80,40],[40],[40,1],[1]; bn1 gamma,beta [H+D];
+ * fc1 [H+D,200],[200]; fc2 [200,80],[80]; fc3 [80,1],[1].  Every tensor starts on a 4-float boundary. */
+int hpmn_param_tensors(const hpmn_shape* s);                          /* number of tensors, <0 on bad shape */
+int64_t hpmn_param_count(const hpmn_shape* s);                        /* floats in the flat buffer */
+int hpmn_param_offsets(const hpmn_shape* s, int64_t* offsets, int64_t* sizes, int n);
+size_t hpmn_workspace_bytes(const hpmn_shape* s, int for_bwd);        /* scratch + saved activations */
+
+/* ---- K1 / K5: embedding gather and its adjoint (code/hpmn.py:414-430, 266-282, 288-289) ---- */
+/* ids [B,T,F] int32, table [V,E] -> x [B,T+front_pad,F*E] (front pad rows and masked ids are zeros) */
+int hpmn_gather_fwd(hpmn_ctx*, const hpmn_shape*, const int32_t* ids, const float* table, float* x,
+                    void* stream);
+/* dtable[ids] += dx rows (+ dlast [B,F*E] on the target step when dlast != NULL); dtable is accumulated */
+int hpmn_gather_bwd(hpmn_ctx*, const hpmn_shape*, const int32_t* ids, const float* dx,
+                    const float* dlast, float* dtable, void* stream);
+
+/* ---- K2 / K4: hierarchical periodic memory (code/hpmn.py:113-131; cell code/util.py:81-110) -- */
+/* x [B,Tpad,D], params flat -> memory [B,L,H]; activations for the adjoint are kept in workspace */
+int hpmn_memory_fwd(hpmn_ctx*, const hpmn_shape*, const float* x, const float* params, float* memory,
+                    void* workspace, void* stream);
+/* dmemory [B,L,H] -> dx [B,Tpad,D] (overwritten), GRU entries of grads (accumulated) */
+int hpmn_memory_bwd(hpmn_ctx*, const hpmn_shape*, const float* x, const float* params,
+                    const float* dmemory, float* dx, float* grads, void* workspace, void* stream);
+
+/* ---- K3: covariance regulariser + multi-hop memory attention (code/hpmn.py:161-182, 133-146) - */
+/* memory [B,L,H], x (for last = x[:, -last_offset]) -> repre [B,H+D] = [q | last], w_hop0 [B,L],
+ * scalars[HPMN_S_COVREG] += sum_b ||offdiag cov||_F  (scalars must be zeroed by the caller) */
+int hpmn_attn_fwd(hpmn_ctx*, const hpmn_shape*, const float* memory, const float* x, const float* params,
+                  float* repre, float* w_hop0, float* scalars, void* workspace, void* stream);
+/* drepre [B,H+D] -> dmemory [B,L,H] (overwritten, includes memory_reg * d covreg), dlast [B,D]
+ * (overwritten), attention entries of grads (accumulated) */
+int hpmn_attn_bwd(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const float* memory, const float* x,
+                  const float* params, const float* drepre, float* dmemory, float* dlast, float* grads,
+                  void* workspace, void* stream);
+
+/* ---- head: BN(inference) -> 200 ELU -> 80 ELU -> 1 sigmoid, log-loss (code/hpmn.py:190-202) -- */
+int hpmn_head_fwd(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const float* repre,
+                  const int32_t* labels, const float* params, float* pred, float* logit, float* scalars,
+                  void* workspace, void* stream);
+int hpmn_head_bwd(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const float* repre,
+                  const int32_t* labels, const float* params, float* drepre, float* grads,
+                  void* workspace, void* stream);
+
+/* ---- whole path: what `sess.run` does (code/hpmn.py:365-367 eval, :336/:482 train, minus Adam) */
+typedef struct hpmn_outputs {  /* each pointer may be NULL except scalars */
+  float* scalars;  /* [4]  HPMN_S_* */
+  float* pred;     /* [B]  sigmoid probability = self.prediction (code/hpmn.py:197) */
+  float* logit;    /* [B]  pre-sigmoid fc3 */
+  float* w_hop0;   /* [B,L] self.user_weights (code/hpmn.py:182,293) */
+  float* memory;   /* [B,L,H] */
+} hpmn_outputs;
+
+/* device buffers in, device buffers out, asynchronous on `stream` */
+int hpmn_forward(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids, const int32_t* labels,
+                 const float* params, const float* table, const hpmn_outputs* out, void* workspace,
+                 void* stream);
+/* + gradients of loss = logloss + memory_reg*covreg (+ l2): grads (flat, OVERWRITTEN), dtable [V,E]
+ * (OVERWRITTEN when zero_dtable != 0, else accumulated) -- tf.gradients at code/hpmn.py:211 before the clip */
+int hpmn_forward_backward(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids,
+                          const int32_t* labels, const float* params, const float* table, float* grads,
+                          float* dtable, int zero_dtable, const hpmn_outputs* out, void* workspace,
+                          void* stream);
+/* same, but ids / labels / outputs are HOST buffers (pinned for truly async copies): H2D of the feed,
+ * compute, D2H of the fetched results, then a stream synchronise -- the feed_dict / fetches round trip
+ * of code/hpmn.py:474-482.  with_backward = 0 is the eval fetch of code/hpmn.py:511-513. */
+int hpmn_step_host(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids_host,
+                   const int32_t* labels_host, const float* params, const float* table, float* grads,
+                   float* dtable, int zero_dtable, int with_backward, const hpmn_outputs* out_host,
+                   void* workspace, void* stream);
+
+/* ---- update step: clip_by_value(g,-1,1) + dense Adam (code/hpmn.py:209-214) ---------------- */
+/* var, m, v updated in place over n floats; t = 1-based step; TF1.4 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t) */
+int hpmn_clip_adam(hpmn_ctx*, float* var, const float* grad, float* m, float* v, int64_t n, int64_t t,
+                   float lr, float beta1, float beta2, float eps, float clip, void* stream);
+
+/* ---- measurement support ------------------------------------------------------------------ */
+/* When enabled, hpmn_forward_backward brackets each kernel family with CUDA events on `stream` and
+ * accumulates their durations (read back with hpmn_profile_read, which synchronises the events). */
+enum { HPMN_K_GATHER = 0, HPMN_K_INPROJ, HPMN_K_REC_FWD, HPMN_K_ATTN_FWD, HPMN_K_HEAD_FWD, HPMN_K_HEAD_BWD,
+       HPMN_K_ATTN_BWD, HPMN_K_REC_BWD, HPMN_K_DX, HPMN_K_WGRAD, HPMN_K_SCATTER, HPMN_K_MISC, HPMN_K_COUNT };
+int hpmn_profile_enable(hpmn_ctx*, int on);
+/* ms[HPMN_K_COUNT] = accumulated milliseconds, calls[HPMN_K_COUNT] = brackets accumulated; resets */
+int hpmn_profile_read(hpmn_ctx*, float* ms, int64_t* calls);
+const char* hpmn_kernel_family_name(int family);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPMN_B200_H */
