@@ -216,9 +216,14 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // exp via ex2.approx (<= 2 ulp) -- error ~1e-7 relative, far inside the 1e-4 parity budget
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-  // 1 - 2/(1+e^{2x}); saturates cleanly for |x| large (e^{2x} -> inf gives 1, -> 0 gives -1)
-  float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, 1.0f + e);
+  // |x| >= 0.15: 1 - 2/(1+e^{2x}) (saturates cleanly: e^{2x} -> inf gives 1, -> 0 gives -1).
+  // |x| <  0.15: odd Taylor series to x^7 (next term < 1e-9 relative) -- the closed form cancels there and
+  // would carry ~1e-7 ABSOLUTE error into values of size 1e-3, i.e. 1e-4 relative.
+  const float e = __expf(2.0f * x);
+  const float big = 1.0f - __fdividef(2.0f, 1.0f + e);
+  const float x2 = x * x;
+  const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -17.0f / 315.0f, 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
+  return fabsf(x) < 0.15f ? small : big;
 }
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 r;

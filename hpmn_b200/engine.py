@@ -126,17 +126,28 @@ class HpmnEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _cshape(self, B: int):
+        """The engine is sized for shape.B rows; any smaller batch reuses the same buffers (the TF graph of the
+        reference has a `None` batch dimension, hpmn.py:248-263)."""
+        if B == self.shape.B:
+            return self.cshape
+        if B <= 0 or B > self.shape.B:
+            raise ValueError("batch %d outside (0, %d]" % (B, self.shape.B))
+        c = self.shape.to_c()
+        c.B = B
+        return c
+
     def forward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0):
         """ids [B,T,F] int32 cuda, labels [B] int32 cuda; results land in self.pred / logit / w_hop0 / scalars."""
         hy = self._hyper(keep_prob, seed, loss_batch)
-        _lib.check(self.lib.hpmn_forward(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(ids), _ptr(labels),
+        _lib.check(self.lib.hpmn_forward(self.ctx, C.byref(self._cshape(ids.shape[0])), C.byref(hy), _ptr(ids), _ptr(labels),
                                          _ptr(self.params), _ptr(self.table), C.byref(self._out), _ptr(self.workspace),
                                          self._stream()), self.ctx)
 
     def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0,
                          loss_batch: int = 0, zero_dtable: bool = True):
         hy = self._hyper(keep_prob, seed, loss_batch)
-        _lib.check(self.lib.hpmn_forward_backward(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(ids), _ptr(labels),
+        _lib.check(self.lib.hpmn_forward_backward(self.ctx, C.byref(self._cshape(ids.shape[0])), C.byref(hy), _ptr(ids), _ptr(labels),
                                                   _ptr(self.params), _ptr(self.table), _ptr(self.grads), _ptr(self.dtable),
                                                   int(zero_dtable), C.byref(self._out), _ptr(self.workspace),
                                                   self._stream()), self.ctx)
@@ -144,19 +155,21 @@ class HpmnEngine:
     def step_host(self, ids: np.ndarray, labels: np.ndarray, with_backward: bool = True, keep_prob: float = 1.0,
                   seed: int = 0, loss_batch: int = 0, zero_dtable: bool = True):
         """Host buffers in, host results out (pinned staging, H2D + compute + D2H + stream sync inside)."""
-        self.h_ids.numpy()[...] = ids
-        self.h_labels.numpy()[...] = labels
-        return self.step_host_pinned(with_backward, keep_prob, seed, loss_batch, zero_dtable)
+        B = int(np.shape(ids)[0])
+        self.h_ids.numpy().reshape(-1)[: B * self.shape.T * self.shape.F] = np.asarray(ids, dtype=np.int32).reshape(-1)
+        self.h_labels.numpy()[:B] = np.asarray(labels, dtype=np.int32)
+        return self.step_host_pinned(with_backward, keep_prob, seed, loss_batch, zero_dtable, B)
 
     def step_host_pinned(self, with_backward: bool = True, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0,
-                         zero_dtable: bool = True):
-        """Same, with the feed already in self.h_ids / self.h_labels."""
+                         zero_dtable: bool = True, B: Optional[int] = None):
+        """Same, with the feed already in self.h_ids / self.h_labels (first B rows, contiguous)."""
+        B = self.shape.B if B is None else B
         hy = self._hyper(keep_prob, seed, loss_batch)
-        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self.cshape), C.byref(hy), _ptr(self.h_ids),
+        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self._cshape(B)), C.byref(hy), _ptr(self.h_ids),
                                            _ptr(self.h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
                                            _ptr(self.dtable), int(zero_dtable), int(with_backward),
                                            C.byref(self._out_host), _ptr(self.workspace), self._stream()), self.ctx)
-        return self.h_scalars.numpy(), self.h_pred.numpy()
+        return self.h_scalars.numpy(), self.h_pred.numpy()[:B]
 
     def apply_gradients(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, clip: float = 1.0):
         """clip_by_value(g,-1,1) + dense Adam over [dense params | table] (hpmn.py:209-214; the clip densifies the

@@ -1,0 +1,205 @@
+"""Python-3 mirror of the reference's model classes (/root/reference/code/hpmn.py:16-560): same class
+names, constructor signatures, methods and log / dump formats, with the TF1 session replaced by
+HpmnEngine (libhpmn_b200.so).  `sess.run(train_step)` becomes engine.step_host + apply_gradients;
+`sess.run([memory_loss, prediction])` becomes engine.step_host(with_backward=False).
+
+Scope of this build: the `user=True, item=False` graph every reference configuration runs
+(hpmn.py:591-592, 619-620, 658-659).  The item-side memory is built by the reference but pruned at run
+time when item=False (hpmn.py:452-462); it is not instantiated here."""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .data_loader import DataLoader, DataLoader_Mul
+from .engine import HpmnEngine
+from .layout import HpmnShape
+
+
+def _metrics(labels, preds):
+    from sklearn.metrics import log_loss, roc_auc_score   # same host-side metrics as hpmn.py:371-372
+    return roc_auc_score(labels, preds), log_loss(labels, preds)
+
+
+class Hpmn_Basic(object):
+    """hpmn.py:16-214.  Subclasses define the variant (front padding, id-0 mask, target position, loader)."""
+
+    front_pad = 0          # zero steps prepended to the user sequence
+    mask_id0 = True        # embedding of id 0 forced to zeros
+    last_offset = 1        # target step counted from the end
+    eval_every = 100       # hpmn.py:483 (Hpmn) / :338 (Hpmn_Industry)
+    loader_cls = DataLoader
+
+    def __init__(self, path, trainset, testset, feature_size, user_dim, item_dim, learning_rate, hidden_size,
+                 embedding_size, hop, user_layers, item_layers, user_num_layers, item_num_layers, user, item,
+                 emb_initializer=None, l2_reg=0, memory_reg=1e-5, max_batch=2048, device=0, seed=4321):
+        if not user or item:
+            raise NotImplementedError("this build implements the user=True, item=False graph the reference runs")
+        self._path = path
+        self.trainset, self.testset = trainset, testset
+        self._save_path = None
+        self.feature_size = feature_size
+        self.learning_rate = learning_rate
+        self.l2_reg, self.memory_reg = l2_reg, memory_reg
+        self.hidden_size, self.embedding_size, self.hop = hidden_size, embedding_size, hop
+        self.emb_initializer = emb_initializer
+        self.user_layers, self.item_layers = user_layers, item_layers
+        self.user_num_layers, self.item_num_layers = user_num_layers, item_num_layers
+        self.user_dim, self.item_dim = user_dim, item_dim
+        self.user, self.item = user, item
+        self.max_batch = max_batch
+        self._device, self._seed = device, seed
+        self._step_seed = 0
+        self.define_inputs()
+        self.build_graph()
+
+    # ---- hpmn.py:64-72
+    @property
+    def save_path(self):
+        if self._save_path is None:
+            save_path = "%s/ckpt" % self._path
+            os.makedirs(save_path, exist_ok=True)
+            self._save_path = os.path.join(save_path, "model.ckpt")
+        return self._save_path
+
+    def define_inputs(self):
+        raise NotImplementedError
+
+    def build_graph(self):
+        """hpmn.py:432-465 / 284-320: here the "graph" is the shape handed to the engine."""
+        self.shape = HpmnShape(B=self.max_batch, T=self.user_maxlen, F=self.user_dim, E=self.embedding_size,
+                               H=self.hidden_size, periods=list(self.user_layers), L=self.user_num_layers, hops=self.hop,
+                               V=self.feature_size, front_pad=self.front_pad, mask_id0=self.mask_id0,
+                               last_offset=self.last_offset)
+        self.shape.steps()   # raises like TF's reshape would when a length is not divisible by its period
+        self.engine = HpmnEngine(self.shape, device=self._device, memory_reg=self.memory_reg, l2_reg=self.l2_reg,
+                                 table=self.emb_initializer, seed=self._seed)
+
+    # ---- hpmn.py:91-111
+    def save_model(self, global_step=None):
+        state = {"step": self.engine.adam_t, "table": self.engine.table.cpu(), "params": self.engine.named_parameters()}
+        path = self.save_path if global_step is None else "%s-%d" % (self.save_path, global_step)
+        torch.save(state, path)
+
+    def load_model(self):
+        try:
+            state = torch.load(self.save_path, weights_only=False)
+            self.engine.load_named(state["params"])
+            self.engine.table.copy_(state["table"])
+        except Exception:
+            raise IOError("Failed to load model from save path: %s" % self.save_path)
+        print("Successfully load model from save path: %s" % self.save_path)
+
+    def log(self, step, result):
+        print("Step: %s\tTrain AUC: %.5f\tTrain Loss: %.5f\tTrain Mem_loss: %.5f"
+              "\tTest AUC: %.5f\tTest Loss: %.5f\tTest Mem_loss: %.5f" % ((str(step),) + tuple(result[:6])))
+        os.makedirs(self._path, exist_ok=True)
+        with open(self._path + "/result.log", "a") as fout:
+            fout.write("%s\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\n" % ((str(step),) + tuple(result[:6])))
+
+    # ---- the two sess.run calls
+    def _feed(self, data):
+        """feed_dict of hpmn.py:474-481: `user_inp` is fed data[1] (the item_part of the tuple)."""
+        return np.asarray(data[1], dtype=np.int32), np.asarray(data[0], dtype=np.int32)
+
+    def train_on_batch(self, data):
+        ids, labels = self._feed(data)
+        self._step_seed += 1
+        self.engine.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=self._step_seed)   # hpmn.py:480
+        self.engine.apply_gradients(self.learning_rate)                                                # hpmn.py:209-214
+
+    def predict_on_batch(self, data):
+        ids, labels = self._feed(data)
+        scalars, pred = self.engine.step_host(ids, labels, with_backward=False, keep_prob=1.0)         # hpmn.py:509
+        return float(scalars[1]), pred.copy(), self.engine.h_w_hop0.numpy()[: len(labels)].copy()
+
+    # ---- hpmn.py:467-495 / 322-349
+    def train(self, epochs, batchsize):
+        step, count, best = 0, 0, 0.0
+        for _ in range(epochs):
+            for _, data in self.loader_cls(self.trainset, batchsize):
+                self.train_on_batch(data)
+                step += 1
+                if step % self.eval_every == 0:
+                    result = list(self.eval(self.trainset, 4 * batchsize))
+                    result += list(self.eval(self.testset, 4 * batchsize))
+                    self.log(step, result)
+                    if result[3] <= best:
+                        count += 1
+                        if count > 3:
+                            return best
+                    else:
+                        count = 0
+                        best = result[3]
+        return best
+
+    # ---- hpmn.py:497-519 / 351-373
+    def eval(self, dataset, batchsize):
+        labels, preds, mem_losses = [], [], []
+        for _, data in self.loader_cls(dataset, batchsize):
+            labels += list(data[0])
+            mem_loss, pred, _ = self.predict_on_batch(data)
+            mem_losses.append(mem_loss)
+            preds += pred.tolist()
+        auc, loss = _metrics(labels, preds)
+        return auc, loss, float(np.average(mem_losses))
+
+
+class Hpmn_Industry(Hpmn_Basic):
+    """hpmn.py:217-410: no id-0 mask, 23 zero steps in front (1001 -> 1024), target = second to last step,
+    XLong TSV loader, eval every 10 steps."""
+
+    front_pad = 23
+    mask_id0 = False
+    last_offset = 2
+    eval_every = 10
+    loader_cls = DataLoader_Mul
+
+    def __init__(self, path, trainset, testset, feature_size, user_dim, item_dim, user_maxlen, item_maxlen,
+                 learning_rate, hidden_size, embedding_size, hop, user_layers, item_layers, user_num_layers,
+                 item_num_layers, user, item, emb_initializer=None, l2_reg=0, memory_reg=1e-5, **kw):
+        self.user_maxlen, self.item_maxlen = user_maxlen, item_maxlen
+        super(Hpmn_Industry, self).__init__(path, trainset, testset, feature_size, user_dim, item_dim, learning_rate,
+                                            hidden_size, embedding_size, hop, user_layers, item_layers, user_num_layers,
+                                            item_num_layers, user, item, emb_initializer, l2_reg, memory_reg, **kw)
+
+    def define_inputs(self):
+        """hpmn.py:247-264: placeholders -> pinned host staging inside the engine."""
+        if self.front_pad:
+            self.front_pad = 1024 - self.user_maxlen if self.user_maxlen <= 1024 else 0   # hpmn.py:288-290 pads to 1024
+
+    # ---- hpmn.py:375-410
+    def get_weights(self):
+        weights, ids = [], []
+        for ds in (self.trainset, self.testset):
+            for _, data in self.loader_cls(ds, 512):
+                _, _, w = self.predict_on_batch(data)
+                weights += w.tolist()
+                ids += np.asarray(data[1])[:, :, 1].tolist()
+        np.save(self._path + "/weights_new.npy", np.array(weights))
+        np.save(self._path + "/ids.npy", np.array(ids))
+
+
+class Hpmn(Hpmn_Industry):
+    """hpmn.py:413-560: id-0 mask, no front padding, target = last step, in-memory loader, eval every 100 steps."""
+
+    front_pad = 0
+    mask_id0 = True
+    last_offset = 1
+    eval_every = 100
+    loader_cls = DataLoader
+
+    def get_weights(self):
+        weights, lengths, labels = [], [], []
+        for ds in (self.trainset, self.testset):
+            for _, data in self.loader_cls(ds, 512):
+                _, _, w = self.predict_on_batch(data)
+                weights += w.tolist()
+                lengths += list(data[2])
+                labels += list(data[0])
+        np.save(self._path + "/weights.npy", np.array(weights))
+        np.save(self._path + "/lengths.npy", np.array(lengths))
+        np.save(self._path + "/labels.npy", labels)

@@ -340,11 +340,13 @@ def gru_layer_bwd(x, hs, rs, us, cs, Wg, Wc, dhs):
 
 
 def backward(sh: OracleShape, fwd, ids, labels, memory_reg=1e-5, l2_reg=0.0, keep_prob=1.0,
-             masks=None, loss_scale_B: Optional[int] = None):
+             masks=None, loss_scale_B: Optional[int] = None, guard_zero_norm: bool = False):
     """Gradient of `loss` w.r.t. every trainable variable (tf.gradients at hpmn.py:211) BEFORE the
     clip of hpmn.py:212.  Returns (grads dict, dtable [V,E] dense -- the clip densifies the
     IndexedSlices in TF1.4).  loss_scale_B: batch size the log-loss mean divides by (the global
-    batch when a rank only holds a shard); default: local B."""
+    batch when a rank only holds a shard); default: local B.
+    guard_zero_norm: tf.norm's gradient is 0/0 = NaN when a sample's off-diagonal covariance is exactly zero
+    (always the case for L == 1); False reproduces that, True yields 0 like the CUDA path."""
     p, tb, gru_saved, cov_saved, att_saved, head_saved = fwd["_saved"]
     dt = tb.dtype
     B = ids.shape[0]
@@ -424,6 +426,8 @@ def backward(sh: OracleShape, fwd, ids, labels, memory_reg=1e-5, l2_reg=0.0, kee
     mc, off, nrm = cov_saved
     with np.errstate(divide="ignore", invalid="ignore"):
         dC = off / nrm[:, None, None]           # 0/0 -> nan exactly as tf.norm's gradient would
+    if guard_zero_norm:
+        dC = np.where(nrm[:, None, None] > 0, dC, 0.0)
     dmc = dt.type(2.0) * (dC @ mc) / dt.type(H)
     dmem += dt.type(memory_reg) * (dmc - dmc.mean(axis=2, keepdims=True))
 

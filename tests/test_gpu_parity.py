@@ -1,0 +1,307 @@
+"""-m gpu: the CUDA path (called through the C ABI of libhpmn_b200.so) against the oracle on identical
+seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full sizes -- through
+size-independent properties.
+
+Tolerances (north_star: logits within 1e-4 relative of the fp32 reference):
+  forward outputs  |d| <= 1e-4*|ref| + 1e-6   (an absolute floor of 1e-6 ~ 8 fp32 ulps at magnitude 1: outputs
+                   that cancel to ~0 carry that much round-off in ANY fp32 evaluation, incl. the fp32 oracle)
+  gradients        ||d||_2 <= 1e-3 * (||ref||_2 + 1e-4 * max_tensor ||ref||_inf)   per tensor
+  gather           bit-exact
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from hpmn_b200.layout import HpmnShape
+from oracle import hpmn_oracle as O
+from oracle import make_golden
+from tests._parity import oracle_shape
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+RTOL, ATOL = 1e-4, 1e-6
+GTOL = 1e-3
+
+
+def _close(a, ref, name):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    bad = np.abs(a - ref) - (RTOL * np.abs(ref) + ATOL)
+    assert bad.max() <= 0, "%s: max |d| %.3e at ref %.3e" % (name, np.abs(a - ref).max(), np.abs(ref).reshape(-1)[np.argmax(bad)])
+
+
+def _grad_close(got, ref, extra=()):
+    gmax = max(np.abs(v).max() for v in ref.values())
+    for k, v in ref.items():
+        err = np.linalg.norm(got[k].astype(np.float64) - v)
+        assert err <= GTOL * (np.linalg.norm(v) + 1e-4 * gmax), "%s: %.3e vs ||ref|| %.3e" % (k, err, np.linalg.norm(v))
+
+
+def _engine(sh, params, table, memory_reg):
+    from hpmn_b200.engine import HpmnEngine
+    return HpmnEngine(sh, device=0, memory_reg=memory_reg, table=table, params=params)
+
+
+CASES = {
+    "amazon_ref_F3_H32": (HpmnShape(B=9, T=20, F=3, E=16, H=32, periods=[2, 5], L=3, hops=3, V=500), True),
+    "amazon_synth_H18": (HpmnShape(B=8, T=20, F=2, E=16, H=18, periods=[2, 2], L=3, hops=3, V=500), True),
+    "industry_pad_last2": (HpmnShape(B=6, T=29, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=300, front_pad=3,
+                                     mask_id0=False, last_offset=2), False),
+    "taobao_ref_F4": (HpmnShape(B=5, T=36, F=4, E=16, H=32, periods=[2, 2, 3], L=4, hops=2, V=400), True),
+    "single_layer_E8_H16": (HpmnShape(B=3, T=7, F=2, E=8, H=16, periods=[], L=1, hops=1, V=50), True),
+    "one_sample_ragged_T": (HpmnShape(B=1, T=18, F=2, E=16, H=32, periods=[3, 2], L=3, hops=3, V=64), True),
+    "many_rows_B67": (HpmnShape(B=67, T=16, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=97), True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("mode", ["stress", "tf_default"])
+def test_forward_backward_matches_oracle(name, mode):
+    import torch
+    sh, ragged = CASES[name]
+    osh = oracle_shape(sh)
+    mreg = 1e-3
+    params, table = O.init_params(osh, seed=4321, mode=mode, dtype=np.float32)
+    ids, labels = O.synthetic_batch(osh, seed=1234, ragged=ragged)
+    fwd = O.forward(osh, params, table, ids, labels, memory_reg=mreg, dtype=np.float64)
+    g_ref, dt_ref = O.backward(osh, fwd, ids, labels, memory_reg=mreg, guard_zero_norm=(sh.L == 1))
+    eng = _engine(sh, params, table, mreg)
+    eng.forward_backward(torch.as_tensor(ids, device=eng.device), torch.as_tensor(labels, device=eng.device))
+    torch.cuda.synchronize()
+    _close(eng.memory.cpu().numpy(), fwd["memory"], "memory")
+    _close(eng.logit.cpu().numpy(), fwd["logit"], "logit")
+    _close(eng.pred.cpu().numpy(), fwd["pred"], "pred")
+    _close(eng.w_hop0.cpu().numpy(), fwd["w_hop0"], "w_hop0")
+    s = eng.scalars.cpu().numpy()
+    _close(s[:3], [fwd["logloss"], fwd["covreg"], fwd["loss"]], "scalars")
+    assert s[3] == 0
+    g_ref = dict(g_ref); g_ref["Embedding/emb_mtx"] = dt_ref
+    got = eng.named_grads(); got["Embedding/emb_mtx"] = eng.dtable.cpu().numpy()
+    _grad_close(got, g_ref)
+    assert eng.launch_count() > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_against_committed_golden_vectors(name):
+    """tests/golden/*.npz were written by the fp64 oracle (oracle/make_golden.py); inputs come from the seeds."""
+    import torch
+    kw, mreg, mode, ragged = make_golden.CASES[name]
+    osh = O.OracleShape(**kw)
+    sh = HpmnShape(B=osh.B, T=osh.T, F=osh.F, E=osh.E, H=osh.H, periods=list(osh.periods), L=osh.L, hops=osh.hops,
+                   V=osh.V, front_pad=osh.front_pad, mask_id0=osh.mask_id0, last_offset=osh.last_offset)
+    params, table = O.init_params(osh, seed=4321, mode=mode, dtype=np.float32)
+    ids, labels = O.synthetic_batch(osh, seed=1234, ragged=ragged)
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    assert int(ids.astype(np.int64).sum()) == int(gold["ids_checksum"])
+    eng = _engine(sh, params, table, mreg)
+    scal, pred = eng.step_host(ids, labels, with_backward=True)          # host buffers in, host results out
+    _close(pred, gold["pred"], "pred")
+    _close(eng.h_logit.numpy(), gold["logit"], "logit")
+    _close(eng.h_w_hop0.numpy(), gold["w_hop0"], "w_hop0")
+    _close(scal[:3], [gold["logloss"], gold["covreg"], gold["loss"]], "scalars")
+    ref = {k[5:]: gold[k] for k in gold.files if k.startswith("grad:")}
+    got = eng.named_grads()
+    ref["Embedding/emb_mtx[touched rows]"] = gold["dtable_rows"]
+    got["Embedding/emb_mtx[touched rows]"] = eng.dtable.cpu().numpy()[np.unique(ids)]
+    _grad_close(got, ref)
+    untouched = np.setdiff1d(np.arange(osh.V), np.unique(ids))
+    assert not eng.dtable.cpu().numpy()[untouched].any()
+    eng.close()
+
+
+def test_gather_is_bit_exact_and_masks():
+    import torch
+    from hpmn_b200 import _lib
+    lib = _lib.lib()
+    for sh in (HpmnShape(B=7, T=33, F=3, E=16, H=32, periods=[3], L=2, hops=1, V=1000),
+               HpmnShape(B=4, T=29, F=2, E=16, H=32, periods=[2], L=2, hops=1, V=1000, front_pad=3, mask_id0=False)):
+        osh = oracle_shape(sh)
+        _, table = O.init_params(osh, mode="stress")
+        ids, _ = O.synthetic_batch(osh, ragged=True)
+        ctx = C.c_void_p(); _lib.check(lib.hpmn_create(C.byref(ctx), 0))
+        d_ids = torch.as_tensor(ids, device="cuda"); d_tab = torch.as_tensor(table, device="cuda")
+        x = torch.full((sh.B, sh.Tpad, sh.D), 7.0, device="cuda")
+        c = sh.to_c()
+        _lib.check(lib.hpmn_gather_fwd(ctx, C.byref(c), d_ids.data_ptr(), d_tab.data_ptr(), x.data_ptr(), None), ctx)
+        torch.cuda.synchronize()
+        assert np.array_equal(x.cpu().numpy(), O.embed(osh, table, ids))
+        # adjoint: scatter-add of ones counts id occurrences
+        dx = torch.ones_like(x); dtab = torch.zeros_like(d_tab)
+        _lib.check(lib.hpmn_gather_bwd(ctx, C.byref(c), d_ids.data_ptr(), dx.data_ptr(), None, dtab.data_ptr(), None), ctx)
+        torch.cuda.synchronize()
+        cnt = np.bincount(ids.reshape(-1), minlength=sh.V).astype(np.float32)
+        if sh.mask_id0:
+            cnt[0] = 0
+        assert np.array_equal(dtab.cpu().numpy(), np.repeat(cnt[:, None], sh.E, 1))
+        lib.hpmn_destroy(ctx)
+
+
+def test_out_of_range_id_is_reported_by_host_entry():
+    from hpmn_b200 import _lib
+    sh = HpmnShape(B=2, T=8, F=2, E=16, H=32, periods=[2], L=2, hops=1, V=50)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh)
+    ids, labels = O.synthetic_batch(osh)
+    ids[1, 3, 1] = 50
+    eng = _engine(sh, params, table, 1e-5)
+    with pytest.raises(_lib.HpmnError, match="feature_size"):
+        eng.step_host(ids, labels)
+    eng.close()
+
+
+def test_smaller_batch_reuses_engine_and_dropout_is_deterministic():
+    import torch
+    sh = HpmnShape(B=16, T=12, F=2, E=16, H=32, periods=[2, 3], L=3, hops=2, V=80)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    ids, labels = O.synthetic_batch(osh)
+    eng = _engine(sh, params, table, 1e-3)
+    _, p_full = eng.step_host(ids, labels, with_backward=False)
+    p_full = p_full.copy()
+    _, p_part = eng.step_host(ids[:5], labels[:5], with_backward=False)
+    assert np.array_equal(p_part, p_full[:5])                       # rows are independent
+    _, a = eng.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=11); a = a.copy(); ga = eng.grads.clone()
+    _, b = eng.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=11)
+    assert np.array_equal(a, b) and not np.array_equal(a, p_full)
+    _, c = eng.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=12)
+    assert not np.array_equal(a, c)
+    assert torch.isfinite(ga).all()
+    eng.close()
+
+
+def _keep_mask(seed, layer, B, units, keep_prob):
+    """Host restatement of dropout_keep() in hpmn_b200/csrc/common.cuh (counter-based SplitMix64 hash)."""
+    M = (1 << 64) - 1
+    out = np.zeros((B, units))
+    for b in range(B):
+        for u in range(units):
+            z = (seed + 0x9E3779B97F4A7C15 * (layer * (1 << 32) + (b << 10) + u + 1)) & M
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+            z = z ^ (z >> 31)
+            out[b, u] = 1.0 if (z >> 40) / 16777216.0 < keep_prob else 0.0
+    return out
+
+
+def test_dropout_matches_oracle_with_replayed_masks():
+    """keep_prob = 0.5 (the training feed, hpmn.py:480): TF's RNG stream cannot be matched, so the kernel's
+    counter-based keep masks are restated on the host and handed to the oracle (tf.nn.dropout scaling 1/keep_prob)."""
+    import torch
+    sh = HpmnShape(B=6, T=12, F=2, E=16, H=32, periods=[2, 3], L=3, hops=2, V=80)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    ids, labels = O.synthetic_batch(osh)
+    masks = (_keep_mask(5, 0, sh.B, 200, 0.5), _keep_mask(5, 1, sh.B, 80, 0.5))
+    assert 0.35 < masks[0].mean() < 0.65
+    f = O.forward(osh, params, table, ids, labels, memory_reg=1e-3, keep_prob=0.5, masks=masks)
+    g_ref, dt_ref = O.backward(osh, f, ids, labels, memory_reg=1e-3, keep_prob=0.5, masks=masks)
+    eng = _engine(sh, params, table, 1e-3)
+    eng.forward_backward(torch.as_tensor(ids, device="cuda"), torch.as_tensor(labels, device="cuda"), keep_prob=0.5, seed=5)
+    torch.cuda.synchronize()
+    _close(eng.logit.cpu().numpy(), f["logit"], "logit (dropout)")
+    g_ref = dict(g_ref); g_ref["Embedding/emb_mtx"] = dt_ref
+    got = eng.named_grads(); got["Embedding/emb_mtx"] = eng.dtable.cpu().numpy()
+    _grad_close(got, g_ref)
+    eng.close()
+
+
+def test_clip_adam_matches_oracle():
+    import torch
+    sh = HpmnShape(B=4, T=8, F=2, E=16, H=32, periods=[2], L=2, hops=1, V=40)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    ids, labels = O.synthetic_batch(osh)
+    eng = _engine(sh, params, table, 1e-3)
+    var = eng.flat.cpu().numpy().astype(np.float64)
+    m = np.zeros_like(var); v = np.zeros_like(var)
+    for t in (1, 2, 3):
+        eng.step_host(ids, labels, with_backward=True)
+        g = eng.flat_grad.cpu().numpy().astype(np.float64) * 50.0      # scale so that the clip at +-1 is active
+        eng.flat_grad.mul_(50.0)
+        assert (np.abs(g) > 1).any()
+        O.clip_adam_step(var, g, m, v, t, lr=0.003)
+        eng.apply_gradients(0.003)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(eng.flat.cpu().numpy(), var, rtol=2e-5, atol=2e-6)
+    eng.close()
+
+
+# ---- full-size properties (BASELINE.json configs) ---------------------------------------------------
+
+XLONG = HpmnShape(B=256, T=1001, F=2, E=16, H=32, periods=[2, 2, 2, 2], L=5, hops=3, V=3308019, front_pad=23,
+                  mask_id0=False, last_offset=2)
+TAOBAO = HpmnShape(B=256, T=300, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=4000000, front_pad=4)
+
+
+@pytest.mark.parametrize("sh", [XLONG, TAOBAO], ids=["xlong", "taobao"])
+def test_full_size_properties(sh):
+    """(1) rows are independent: permuting the batch permutes predictions and leaves summed gradients unchanged
+    (up to atomic summation order); (2) accumulating dtable over two identical steps doubles it; (3) oracle parity on
+    the first rows of the very same full-size batch (the oracle handles 2 rows of T=1024 in seconds)."""
+    import torch
+    from hpmn_b200.data_loader import synthetic_ids
+    from hpmn_b200.engine import HpmnEngine
+    eng = HpmnEngine(sh, memory_reg=5e-5, seed=7)
+    for n in eng.layout:                       # leave the default init but make biases non-trivial
+        if n.endswith("bias"):
+            eng.view(n).add_(0.05)
+    ids = synthetic_ids(sh.B, sh.T, sh.F, sh.V, seed=3, ragged=sh.mask_id0)
+    labels = np.random.default_rng(3).integers(0, 2, size=sh.B).astype(np.int32)
+    d_ids = torch.as_tensor(ids, device="cuda"); d_lab = torch.as_tensor(labels, device="cuda")
+    eng.forward_backward(d_ids, d_lab)
+    torch.cuda.synchronize()
+    pred = eng.pred.cpu().numpy().copy(); grads = eng.grads.clone(); dtab = eng.dtable.clone(); scal = eng.scalars.cpu().numpy().copy()
+    assert np.isfinite(pred).all() and ((pred > 0) & (pred < 1)).all() and torch.isfinite(grads).all()
+    perm = np.random.default_rng(4).permutation(sh.B)
+    eng.forward_backward(torch.as_tensor(ids[perm], device="cuda"), torch.as_tensor(labels[perm], device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(eng.pred.cpu().numpy(), pred[perm])
+    assert float((eng.grads - grads).norm() / grads.norm()) < 1e-4
+    assert float((eng.dtable - dtab).norm() / dtab.norm()) < 1e-4
+    np.testing.assert_allclose(eng.scalars.cpu().numpy()[:3], scal[:3], rtol=1e-5)
+    eng.forward_backward(d_ids, d_lab)
+    eng.forward_backward(d_ids, d_lab, zero_dtable=False)
+    torch.cuda.synchronize()
+    assert float((eng.dtable - 2 * dtab).norm() / dtab.norm()) < 1e-4
+    # oracle on rows 0..1 of the same batch (table restricted to the rows they touch)
+    rows = 2
+    sub = ids[:rows]
+    uniq, inv = np.unique(sub, return_inverse=True)
+    small_table = eng.table[torch.as_tensor(uniq, device="cuda").long()].cpu().numpy()
+    osh = O.OracleShape(B=rows, T=sh.T, F=sh.F, E=sh.E, H=sh.H, periods=list(sh.periods), L=sh.L, hops=sh.hops,
+                        V=len(uniq), front_pad=sh.front_pad, mask_id0=False, last_offset=sh.last_offset)
+    sub_ids = inv.reshape(sub.shape).astype(np.int32)
+    params = eng.named_parameters()
+    if sh.mask_id0:                            # emulate the id-0 mask with a zero row
+        small_table = small_table.copy(); small_table[uniq == 0] = 0
+    f = O.forward(osh, params, small_table, sub_ids, labels[:rows], memory_reg=5e-5)
+    _close(pred[:rows], f["pred"], "pred[:2] at full size")
+    eng.close()
+
+
+def test_two_gpu_gradient_equals_single():
+    """DP contract on real GPUs when the box has >= 2: shard rows, loss_batch = global B, one all-reduce."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (covered on CPU by tests/test_dist_gloo.py)")
+    from hpmn_b200.engine import HpmnEngine
+    sh = HpmnShape(B=8, T=16, F=2, E=16, H=32, periods=[2, 2], L=3, hops=2, V=60)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    ids, labels = O.synthetic_batch(osh)
+    full = HpmnEngine(sh, device=0, memory_reg=1e-3, table=table, params=params)
+    full.forward_backward(torch.as_tensor(ids, device="cuda:0"), torch.as_tensor(labels, device="cuda:0"))
+    parts = []
+    for r in range(2):
+        e = HpmnEngine(sh.with_batch(4), device=r, memory_reg=1e-3, table=table, params=params)
+        dev = "cuda:%d" % r
+        e.forward_backward(torch.as_tensor(ids[4 * r: 4 * r + 4], device=dev), torch.as_tensor(labels[4 * r: 4 * r + 4], device=dev),
+                           loss_batch=8)
+        torch.cuda.synchronize(dev)
+        parts.append(e.flat_grad.cpu())
+    tot = parts[0] + parts[1]
+    ref = full.flat_grad.cpu()
+    assert float((tot - ref).norm() / ref.norm()) < 1e-5
