@@ -1,0 +1,299 @@
+"""bench.py -- HPMN fwd+bwd samples/sec on the XLong-shape synthetic workload (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # product arm (libhpmn_b200.so on B200)
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # reference arm: the TF1-equivalent CPU restatement
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # N > 1: one rank per GPU, NCCL all-reduce per step
+
+One "step" = embedding gather -> 5-layer periodic GRU memory -> covreg + 3-hop attention -> head -> log-loss and
+the full backward down to the dense embedding-table gradient (tf.gradients of code/hpmn.py:211; optimizer excluded),
+plus, when N > 1, the single flat gradient all-reduce.  Batch 256 per GPU (weak scaling).
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how each field is produced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+METRIC = "hpmn_fwd_bwd_samples_per_sec_xlong"
+UNIT = "samples/s"
+
+CONFIGS = {
+    # BASELINE.json configs[3]: XLong-shape synthetic (code/hpmn.py:643-662 user side)
+    "xlong": dict(T=1001, F=2, E=16, H=32, periods=[2, 2, 2, 2], L=5, hops=3, V=3308019, front_pad=23, mask_id0=False,
+                  last_offset=2, memory_reg=5e-5, batch=256),
+    # configs[2]: Taobao-shape synthetic (T 300 -> 304)
+    "taobao": dict(T=300, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=4000000, front_pad=4, mask_id0=True,
+                   last_offset=1, memory_reg=1e-5, batch=256),
+    # configs[1]: Amazon-shape synthetic
+    "amazon": dict(T=100, F=2, E=16, H=18, periods=[2, 2], L=3, hops=3, V=65536, front_pad=0, mask_id0=True,
+                   last_offset=1, memory_reg=1e-5, batch=128),
+}
+
+
+def workload_name(cfg_name, cfg, B):
+    return "%s-synthetic B=%d/GPU T=%d->%d F=%d E=%d H=%d L=%d periods=%s hops=%d V=%d" % (
+        cfg_name, B, cfg["T"], cfg["T"] + cfg["front_pad"], cfg["F"], cfg["E"], cfg["H"], cfg["L"], cfg["periods"],
+        cfg["hops"], cfg["V"])
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        inside = [r for (t, r) in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
+        sm = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in inside:
+            for i, n in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(inside)}
+
+
+# --------------------------------------------------------------------------------------------------
+def oracle_inputs(cfg, B, seed_data=1234, seed_params=4321, V_cap=None):
+    from oracle import hpmn_oracle as O
+    V = min(cfg["V"], V_cap) if V_cap else cfg["V"]
+    sh = O.OracleShape(B=B, T=cfg["T"], F=cfg["F"], E=cfg["E"], H=cfg["H"], periods=cfg["periods"], L=cfg["L"],
+                       hops=cfg["hops"], V=V, front_pad=cfg["front_pad"], mask_id0=cfg["mask_id0"],
+                       last_offset=cfg["last_offset"])
+    params, table = O.init_params(sh, seed=seed_params, mode="tf_default")
+    ids, labels = O.synthetic_batch(sh, seed=seed_data, ragged=False)
+    return sh, params, table, ids, labels
+
+
+def run_reference(args, cfg_name, cfg):
+    """Reference arm: the reference's own CPU path.  TF1.4/py2 cannot be installed, so this is the
+    TF1-equivalent restatement (oracle/tf1_restatement.py, kind "port") on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import tf1_restatement as R
+    rows = args.ref_rows
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    # the table only matters through the rows touched; cap V so that the dense autograd table gradient stays cheap
+    sh, params, table, ids, labels = oracle_inputs(cfg, rows, V_cap=400000)
+    p = R._t(params, torch.float32)
+    tb = torch.tensor(table, dtype=torch.float32, requires_grad=True)
+    tid, tl = torch.tensor(ids, dtype=torch.int64), torch.tensor(labels, dtype=torch.float32)
+    times = []
+    for i in range(args.warmup + args.steps):
+        for v in p.values():
+            v.grad = None
+        tb.grad = None
+        t0 = time.perf_counter()
+        out = R.forward_torch(sh, p, tb, tid, tl, memory_reg=cfg["memory_reg"])
+        out["loss"].backward()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = float(sum(times))
+    value = rows * len(times) / total
+    B = args.batch or cfg["batch"]
+    sample = "%d of %d rows per step, full T=%d recurrence, fwd+bwd, fp32 torch-CPU op-per-timestep loop" % (rows, B, cfg["T"] + cfg["front_pad"])
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg_name, cfg, B), "sample_rows_per_step": rows,
+                       "note": "TF1-equivalent restatement, not TensorFlow (TF1.4/py2 not installable; DESIGN.md)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_product(args, cfg_name, cfg):
+    import torch
+    from hpmn_b200 import dist as hd
+    from hpmn_b200.data_loader import synthetic_ids
+    from hpmn_b200.engine import HpmnEngine
+    from hpmn_b200.layout import HpmnShape
+
+    rank, local_rank, world = hd.init_process_group("nccl")
+    if world != args.gpus and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+    B = args.batch or cfg["batch"]
+    sh = HpmnShape(B=B, T=cfg["T"], F=cfg["F"], E=cfg["E"], H=cfg["H"], periods=cfg["periods"], L=cfg["L"],
+                   hops=cfg["hops"], V=cfg["V"], front_pad=cfg["front_pad"], mask_id0=cfg["mask_id0"],
+                   last_offset=cfg["last_offset"])
+    eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321)   # replicated parameters
+    dev = eng.device
+    NB = 8   # distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
+    #          per-step working set is far larger than the 126 MB L2, so no explicit flush is needed
+    h_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + 97 * rank + i)).pin_memory() for i in range(NB)]
+    h_lab = [torch.from_numpy(np.random.default_rng(99 + i + rank).integers(0, 2, size=B).astype(np.int32)).pin_memory()
+             for i in range(NB)]
+    d_ids = [t.to(dev) for t in h_ids]
+    d_lab = [t.to(dev) for t in h_lab]
+    loss_batch = B * world
+
+    def step_dev(i):
+        eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=args.keep_prob, seed=i, loss_batch=loss_batch)
+        if world > 1:
+            hd.allreduce_flat(eng.flat_grad)          # the step's single collective
+
+    def step_host(i):
+        eng.step_host_pinned(True, args.keep_prob, i, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB])
+        if world > 1:
+            hd.allreduce_flat(eng.flat_grad)
+
+    def timed(fn, steps):
+        hd.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev); hd.barrier()
+        w1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)    # max over ranks
+        return float(ms.item()), (w0, w1)
+
+    sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        step_dev(i)
+    for i in range(min(args.warmup, 3)):
+        step_host(i)
+    if rank == 0:
+        sampler.start()
+    windows = []
+    l0 = eng.launch_count()
+    ms_dev, w = timed(step_dev, args.steps); windows.append(w)
+    launches = eng.launch_count() - l0
+    ms_e2e, w = timed(step_host, args.steps); windows.append(w)
+    # per-kernel-family device time: same step, same inputs, CUDA-event brackets on the launch stream
+    eng.profile(True)
+    _, w = timed(step_dev, args.steps); windows.append(w)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop(windows) if rank == 0 else None
+    scal = eng.scalars.cpu().numpy()
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    steps_all = sh.steps()
+    fl_rec_fwd = B * sum(s * 2 * sh.H * 3 * sh.H for s in steps_all)                 # recurrent half, per launch set
+    fl_gru_fwd = B * sh.gru_flops_fwd_per_sample()
+    fams = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
+    gather_bytes = sh.gather_bytes() + B * sh.Tpad * sh.D * 4
+    scatter_bytes = sh.gather_bytes() + 2 * 4 * sh.E * B * sh.T * sh.F
+    if "gather_fwd" in fams:
+        fams["gather_fwd"]["GBps"] = gather_bytes / (fams["gather_fwd"]["ms_per_step"] * 1e-3) / 1e9
+        fams["gather_fwd"]["frac_of_hbm_peak"] = fams["gather_fwd"]["GBps"] / hbm_peak
+    if "scatter_add" in fams:
+        fams["scatter_add"]["GBps"] = scatter_bytes / (fams["scatter_add"]["ms_per_step"] * 1e-3) / 1e9
+        fams["scatter_add"]["frac_of_hbm_peak"] = fams["scatter_add"]["GBps"] / hbm_peak
+    dom = max(fams, key=lambda k: fams[k]["ms_per_step"])
+    dom_ms = fams[dom]["ms_per_step"]
+    flops_by_family = {"rec_fwd": fl_rec_fwd, "rec_bwd": fl_rec_fwd, "inproj_gemm": fl_gru_fwd - fl_rec_fwd,
+                       "dx_gemm": fl_gru_fwd - fl_rec_fwd, "gru_wgrad": fl_gru_fwd}
+    if dom in flops_by_family:
+        achieved = flops_by_family[dom] / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_flops_per_step": flops_by_family[dom], "kernel_ms_per_step": dom_ms,
+                "note": "fp32 FFMA2 kernel (1e-4 parity rules out single-pass tf32/bf16 tensor-core math through 1024 "
+                        "recurrent steps); latency-bound at B=256 -- see DESIGN.md. fp32 CUDA-core peak ~74 TFLOP/s."}
+    else:
+        byts = gather_bytes if dom == "gather_fwd" else scatter_bytes
+        achieved = byts / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms_per_step": dom_ms}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import tf1_restatement as R
+        rows = args.cpu_rows
+        osh, params, table, ids, labels = oracle_inputs(cfg, rows, V_cap=400000)
+        r = R.time_cpu_baseline(osh, params, table, ids, labels, iters=3, warmup=1, budget_s=40)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": "%d of %d rows, full T=%d recurrence, %d timed fwd+bwd passes, fp32 torch-CPU restatement of the TF1 "
+                         "graph (TensorFlow 1.4 itself is not installable here)" % (rows, B, sh.Tpad, r["iters"])}
+    value = B * world * args.steps / (ms_dev * 1e-3)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = B * sh.T * sh.F * 4 + B * 4
+    d2h = 16 + B * 4 * 2 + B * sh.L * 4
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world,
+                       "parallelism": "dp%d batch-sharded, replicated table, one flat all-reduce per step" % world,
+                       "l2": "inputs larger than L2 (212 MB table + 0.56 GB streamed activations per step, %d rotating id batches)" % NB,
+                       "keep_prob": args.keep_prob, "optimizer": "excluded (fwd+bwd metric)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": "hpmn_step_host (C ABI): pinned host ids/labels -> H2D -> fwd+bwd -> D2H scalars,pred,logit,weights -> sync"},
+            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": fams,
+            "check": {"logloss": float(scal[0]), "covreg": float(scal[1])}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="xlong", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the config's)")
+    ap.add_argument("--keep-prob", type=float, default=0.5, help="dropout keep prob of the train feed (code/hpmn.py:480)")
+    ap.add_argument("--cpu-rows", type=int, default=64)
+    ap.add_argument("--ref-rows", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, args.config, cfg)
+    else:
+        run_product(args, args.config, cfg)
+
+
+if __name__ == "__main__":
+    main()

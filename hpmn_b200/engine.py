@@ -161,12 +161,16 @@ class HpmnEngine:
         return self.step_host_pinned(with_backward, keep_prob, seed, loss_batch, zero_dtable, B)
 
     def step_host_pinned(self, with_backward: bool = True, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0,
-                         zero_dtable: bool = True, B: Optional[int] = None):
-        """Same, with the feed already in self.h_ids / self.h_labels (first B rows, contiguous)."""
+                         zero_dtable: bool = True, B: Optional[int] = None, h_ids: Optional[torch.Tensor] = None,
+                         h_labels: Optional[torch.Tensor] = None):
+        """Same, with the feed already in pinned host memory: self.h_ids / self.h_labels (first B rows, contiguous)
+        or caller-owned pinned int32 tensors."""
         B = self.shape.B if B is None else B
+        h_ids = self.h_ids if h_ids is None else h_ids
+        h_labels = self.h_labels if h_labels is None else h_labels
         hy = self._hyper(keep_prob, seed, loss_batch)
-        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self._cshape(B)), C.byref(hy), _ptr(self.h_ids),
-                                           _ptr(self.h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
+        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self._cshape(B)), C.byref(hy), _ptr(h_ids),
+                                           _ptr(h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
                                            _ptr(self.dtable), int(zero_dtable), int(with_backward),
                                            C.byref(self._out_host), _ptr(self.workspace), self._stream()), self.ctx)
         return self.h_scalars.numpy(), self.h_pred.numpy()[:B]
