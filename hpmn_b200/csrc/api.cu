@@ -99,6 +99,8 @@ static int make_plan(hpmn_ctx* ctx, const hpmn_shape* s, void* workspace, Plan& 
   p.d = make_dims(s);
   if (!p.d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape (need E%%4==0, H<=32, L<=16, hops<=8, steps divisible by periods)");
   if (p.d.D > 64) return fail(ctx, HPMN_EINVAL, "F*E = %d > 64 is not supported by this build", p.d.D);
+  for (int k = 0; k + 1 < p.d.L; ++k)
+    if (p.d.P[k] > 16) return fail(ctx, HPMN_EINVAL, "period %d > 16 is not supported by this build", p.d.P[k]);
   p.pl = make_param_layout(p.d);
   p.pk = make_pack_layout(p.d);
   p.wl = make_ws_layout(p.d);
@@ -119,12 +121,12 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   float* pw = p.f(p.wl.pw);
   { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
   for (int k = 0; k < d.L; ++k) {
-    const float* A = k == 0 ? x : p.f(p.wl.hs[k - 1]) + (int64_t)(d.P[k - 1] - 1) * HP;
-    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * HP;
+    const float* A = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;   // every p-th h row
+    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
     { Bracket b(ctx, st, HPMN_K_INPROJ);
       launch_gemm_nn(L, A, lda, pw + p.pk.Wx[k], pw + p.pk.bx[k], p.f(p.wl.proj[k]), (int64_t)d.B * d.S[k], G3, d.DinP[k], st); }
     { Bracket b(ctx, st, HPMN_K_REC_FWD);
-      launch_rec_fwd(L, d, k, p.f(p.wl.proj[k]), pw + p.pk.Wh[k], p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), memory, st); }
+      launch_rec_fwd(L, d, k, p.f(p.wl.proj[k]), pw + p.pk.Wh[k], p.f(p.wl.st[k]), memory, st); }
   }
 }
 
@@ -138,14 +140,14 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
     float* da = p.f(p.wl.proj[k]);
     const float* dx_up = k < d.L - 1 ? p.f(p.wl.dxk[k + 1]) : nullptr;
     { Bracket b(ctx, st, HPMN_K_REC_BWD);
-      launch_rec_bwd(L, d, k, p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), pw + p.pk.WhT[k], dmemory, dx_up, da, st); }
+      launch_rec_bwd(L, d, k, p.f(p.wl.st[k]), pw + p.pk.WhT[k], dmemory, dx_up, da, st); }
     float* dxk = k == 0 ? dx0 : p.f(p.wl.dxk[k]);
     { Bracket b(ctx, st, HPMN_K_DX);
       launch_gemm_nn(L, da, G3, pw + p.pk.WxT[k], nullptr, dxk, (int64_t)d.B * d.S[k], d.DinP[k], G3, st); }
-    const float* A = k == 0 ? x : p.f(p.wl.hs[k - 1]) + (int64_t)(d.P[k - 1] - 1) * HP;
-    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * HP;
+    const float* A = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;   // every p-th h row
+    const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
     { Bracket b(ctx, st, HPMN_K_WGRAD);
-      launch_gru_wgrad(L, d, k, A, lda, p.f(p.wl.hs[k]), p.f(p.wl.gates[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
+      launch_gru_wgrad(L, d, k, A, lda, p.f(p.wl.st[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
                        grads + p.pl.Wc[k], grads + p.pl.bc[k], st); }
   }
 }

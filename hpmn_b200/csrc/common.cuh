@@ -11,6 +11,7 @@ namespace hpmn {
 
 constexpr int HP = 32;        // hidden width padded to one warp (this build: H <= 32)
 constexpr int G3 = 3 * HP;    // r | u | c columns of a packed gate row
+constexpr int ST = 4 * HP;    // h | r | u | c columns of a saved state row
 constexpr int ATT1 = 80;      // code/hpmn.py:137
 constexpr int ATT2 = 40;      // code/hpmn.py:138
 constexpr int FC1 = 200;      // code/hpmn.py:191
@@ -111,8 +112,7 @@ struct WsLayout {
   size_t x;                           // [B,Tpad,D]
   size_t pw;                          // packed weights (see PackLayout), rebuilt every call
   size_t proj[HPMN_MAX_LAYERS];       // [B,S_k,3,HP]  input projections; reused as da in bwd
-  size_t hs[HPMN_MAX_LAYERS];         // [B,S_k,HP]    hidden outputs
-  size_t gates[HPMN_MAX_LAYERS];      // [B,S_k,3,HP]  r,u,c
+  size_t st[HPMN_MAX_LAYERS];         // [B,S_k,4,HP]  per-step state row h | r | u | c  (512 B, one bulk store)
   size_t dxk[HPMN_MAX_LAYERS];        // k>=1: [B,S_k,HP] gradient wrt layer input; k=0: [B,Tpad,D]
   size_t memory, dmemory;             // [B,L,H]
   size_t att_q, att_dq;               // [hops+1][B,H]  query before each hop (+ final) and its gradient
@@ -165,8 +165,7 @@ inline WsLayout make_ws_layout(const Dims& d) {
   for (int k = 0; k < d.L; ++k) {
     size_t rows = (size_t)d.B * d.S[k];
     w.proj[k] = take(rows * G3 * f);
-    w.hs[k] = take(rows * HP * f);
-    w.gates[k] = take(rows * G3 * f);
+    w.st[k] = take(rows * ST * f);
     w.dxk[k] = take(rows * (k == 0 ? d.D : HP) * f);
   }
   w.memory = take((size_t)d.B * d.L * d.H * f);
@@ -234,6 +233,38 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// ---- bulk async copies (TMA engine, SASS UBLKCP) and mbarriers -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  int spins = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();      // a lost transaction must abort, never hang the GPU
+  } while (!done);
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -276,13 +307,12 @@ void atb_add(AtbBatch& batch, int sms, const float* A, int64_t lda, const float*
              int64_t M, int I, int N);
 void launch_atb_batch(const Launch&, const AtbBatch& batch, cudaStream_t st);
 
-void launch_rec_fwd(const Launch&, const Dims&, int k, const float* proj, const float* Wh, float* hs, float* gates,
-                    float* memory, cudaStream_t st);
-void launch_rec_bwd(const Launch&, const Dims&, int k, const float* hs, const float* gates, const float* WhT,
-                    const float* dmemory, const float* dx_up, float* da, cudaStream_t st);
-void launch_gru_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* hs,
-                      const float* gates, const float* da, float* dWg, float* dbg, float* dWc, float* dbc,
-                      cudaStream_t st);
+void launch_rec_fwd(const Launch&, const Dims&, int k, const float* proj, const float* Wh, float* st, float* memory,
+                    cudaStream_t st_);
+void launch_rec_bwd(const Launch&, const Dims&, int k, const float* st, const float* WhT, const float* dmemory,
+                    const float* dx_up, float* da, cudaStream_t st_);
+void launch_gru_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* st, const float* da,
+                      float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_);
 
 // resolved workspace pointers handed to the attention / head kernels
 struct AttWs { float *q, *dq, *w, *ds, *inp, *z1, *dz1, *z2, *dz2; };

@@ -219,8 +219,9 @@ def test_clip_adam_matches_oracle():
     m = np.zeros_like(var); v = np.zeros_like(var)
     for t in (1, 2, 3):
         eng.step_host(ids, labels, with_backward=True)
-        g = eng.flat_grad.cpu().numpy().astype(np.float64) * 50.0      # scale so that the clip at +-1 is active
-        eng.flat_grad.mul_(50.0)
+        scale = 2.0 / float(eng.flat_grad.abs().max())                 # scale so that the clip at +-1 is active
+        g = eng.flat_grad.cpu().numpy().astype(np.float64) * scale
+        eng.flat_grad.mul_(scale)
         assert (np.abs(g) > 1).any()
         O.clip_adam_step(var, g, m, v, t, lr=0.003)
         eng.apply_gradients(0.003)
