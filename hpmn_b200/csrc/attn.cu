@@ -2,9 +2,9 @@
 // memory slots.  Replaces get_covreg / query_memory / attention of
 // /root/reference/code/hpmn.py:161-170, 172-182, 133-146 and their tf.gradients adjoint.
 //
-// One CTA (128 threads) per sample; memory slots, query and the score-MLP activations live in shared
-// memory, softmax over the L <= 16 slots is a warp-shuffle reduction, all hops are fused.  The MLP
-// weights (53 KB per hop) are read through L1/L2 -- every CTA reads the same addresses.  The backward
+// One CTA (256 threads) per sample; memory slots, query, the score-MLP activations AND the current hop's MLP
+// weights (53 KB, staged from L2 into padded shared memory) live on chip, softmax over the L <= 16 slots is a
+// warp-shuffle reduction, all hops are fused, one (slot, unit) output per thread.  The backward
 // kernel emits per-sample deltas only; the weight gradients are reductions over the batch and are
 // queued as one batched A^T*B launch (gemm.cu).
 #include "common.cuh"
@@ -25,31 +25,19 @@ struct AttnArgs {
   int64_t A1[HPMN_MAX_HOPS], a1[HPMN_MAX_HOPS], A2[HPMN_MAX_HOPS], a2[HPMN_MAX_HOPS], A3[HPMN_MAX_HOPS], a3[HPMN_MAX_HOPS];
 };
 
-// y[l][o] = act(bias[o] + sum_i in[l][i] * W[i*NO + o]) for o = tid < NO, all l < L (8 slots at a time)
-template <bool RELU>
-__device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ bias, const float* in,
-                                           int in_ld, int NI, int NO, int L, float* out, int out_ld, float* gout) {
-  const int o = threadIdx.x;
-  if (o >= NO) return;
-  const float bo = __ldg(bias + o);
-  for (int l0 = 0; l0 < L; l0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int ll = 0; ll < 8; ++ll) acc[ll] = bo;
-    for (int i = 0; i < NI; ++i) {
-      const float w = __ldg(W + (int64_t)i * NO + o);
-#pragma unroll
-      for (int ll = 0; ll < 8; ++ll)
-        if (l0 + ll < L) acc[ll] = fmaf(in[(l0 + ll) * in_ld + i], w, acc[ll]);
-    }
-#pragma unroll
-    for (int ll = 0; ll < 8; ++ll)
-      if (l0 + ll < L) {
-        float v = RELU ? fmaxf(acc[ll], 0.f) : acc[ll];
-        out[(l0 + ll) * out_ld + o] = v;
-        gout[(l0 + ll) * out_ld + o] = v;
-      }
-  }
+constexpr int NT = 256;               // threads per CTA
+constexpr int A1S = ATT1 + 1;         // padded row strides of the staged score-MLP weights (bank-conflict free
+constexpr int A2S = ATT2 + 1;         //   for both the forward (column) and the backward (row) access pattern)
+
+// stage one hop's score-MLP weights in shared memory: A1 [4H,80] -> [4H][81], A2 [80,40] -> [80][41], A3 [40]
+__device__ __forceinline__ void stage_weights(const float* __restrict__ P, const AttnArgs& a, int hop, int H4, float* sA1,
+                                              float* sA2, float* sA3, float* sB1, float* sB2) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < H4 * ATT1; e += NT) sA1[(e / ATT1) * A1S + e % ATT1] = __ldg(P + a.A1[hop] + e);
+  for (int e = tid; e < ATT1 * ATT2; e += NT) sA2[(e / ATT2) * A2S + e % ATT2] = __ldg(P + a.A2[hop] + e);
+  if (tid < ATT2) sA3[tid] = __ldg(P + a.A3[hop] + tid);
+  if (tid < ATT1) sB1[tid] = __ldg(P + a.a1[hop] + tid);
+  if (tid < ATT2) sB2[tid] = __ldg(P + a.a2[hop] + tid);
 }
 
 // covariance pieces shared by fwd and bwd: centred memory mean per slot, off-diagonal C, Frobenius norm
@@ -81,20 +69,30 @@ __device__ __forceinline__ float covreg_block(const float (*sM)[HP], float* sMea
   return sqrtf(tot);
 }
 
-__global__ void __launch_bounds__(128)
+// dynamic shared memory carve-up (floats)
+struct AttSmem {
+  float *A1, *A2, *A3, *B1, *B2, *Inp, *Z1, *Z2;
+  __device__ AttSmem(float* base, int H4) {
+    A1 = base; A2 = A1 + H4 * A1S; A3 = A2 + ATT1 * A2S; B1 = A3 + ATT2; B2 = B1 + ATT1;
+    Inp = B2 + ATT2; Z1 = Inp + ML * 4 * HP; Z2 = Z1 + ML * ATT1;
+  }
+  static size_t bytes(int H4) { return sizeof(float) * (size_t)(H4 * A1S + ATT1 * A2S + 2 * ATT2 + ATT1 + ML * 4 * HP + ML * ATT1 + ML * ATT2); }
+};
+
+__global__ void __launch_bounds__(NT)
 attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ __align__(16) float dsm[];
   __shared__ float sM[ML][HP];
   __shared__ float sC[ML][ML];
-  __shared__ float sMean[ML], sRed[4], sS[ML], sW[ML];
+  __shared__ float sMean[ML], sRed[NT / 32], sS[ML], sW[ML];
   __shared__ float sLast[MD], sQ[HP], sQn[HP];
-  __shared__ float sInp[ML * 4 * HP];
-  __shared__ float sZ1[ML * ATT1];
-  __shared__ float sZ2[ML * ATT2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = a.L, H = a.H, D = a.D, B = a.B;
+  const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
+  AttSmem S(dsm, H4);
   const float* P = a.params;
-  for (int e = tid; e < L * H; e += 128) sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e);
-  for (int e = tid; e < D; e += 128) sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
+  for (int e = tid; e < L * H; e += NT) sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e);
+  for (int e = tid; e < D; e += NT) sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
+  stage_weights(P, a, 0, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
   __syncthreads();
   const float nrm = covreg_block(sM, sMean, sC, sRed, L, H);          // hpmn.py:161-170
   if (tid == 0) atomicAdd(a.scalars + HPMN_S_COVREG, nrm);
@@ -105,26 +103,53 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
     a.ws.q[(int64_t)b * H + tid] = q;
   }
   __syncthreads();
-  const int H4 = 4 * H;
   for (int hop = 0; hop < a.hops; ++hop) {
     float* ginp = a.ws.inp + ((int64_t)hop * B + b) * L * H4;
-    for (int e = tid; e < L * H4; e += 128) {                          // hpmn.py:135-136
+    for (int e = tid; e < L * H4; e += NT) {                           // hpmn.py:135-136
       const int l = e / H4, c = e % H4, part = c / H, j = c % H;
       const float q = sQ[j], m = sM[l][j];
       const float v = part == 0 ? q : (part == 1 ? m : (part == 2 ? q - m : q * m));
-      sInp[l * H4 + c] = v;
+      S.Inp[l * H4 + c] = v;
       ginp[e] = v;
     }
     __syncthreads();
-    dense_rows<true>(P + a.A1[hop], P + a.a1[hop], sInp, H4, H4, ATT1, L, sZ1, ATT1,
-                     a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1);     // hpmn.py:137
+    {                                                                  // fc1 (4H -> 80, relu), hpmn.py:137
+      float* gz1 = a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1;
+      for (int w = tid; w < L * ATT1; w += NT) {                       // one (slot, unit) per thread
+        const int l = w / ATT1, o = w % ATT1;
+        const float* in = S.Inp + l * H4;
+        float acc0 = S.B1[o], acc1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < H4; i += 2) {
+          acc0 = fmaf(in[i], S.A1[i * A1S + o], acc0);
+          acc1 = fmaf(in[i + 1], S.A1[(i + 1) * A1S + o], acc1);
+        }
+        const float v = fmaxf(acc0 + acc1, 0.f);
+        S.Z1[l * ATT1 + o] = v;
+        gz1[w] = v;
+      }
+    }
     __syncthreads();
-    dense_rows<true>(P + a.A2[hop], P + a.a2[hop], sZ1, ATT1, ATT1, ATT2, L, sZ2, ATT2,
-                     a.ws.z2 + ((int64_t)hop * B + b) * L * ATT2);     // hpmn.py:138
+    {                                                                  // fc2 (80 -> 40, relu), hpmn.py:138
+      float* gz2 = a.ws.z2 + ((int64_t)hop * B + b) * L * ATT2;
+      for (int w = tid; w < L * ATT2; w += NT) {
+        const int l = w / ATT2, o = w % ATT2;
+        const float* in = S.Z1 + l * ATT1;
+        float acc0 = S.B2[o], acc1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < ATT1; i += 2) {
+          acc0 = fmaf(in[i], S.A2[i * A2S + o], acc0);
+          acc1 = fmaf(in[i + 1], S.A2[(i + 1) * A2S + o], acc1);
+        }
+        const float v = fmaxf(acc0 + acc1, 0.f);
+        S.Z2[l * ATT2 + o] = v;
+        gz2[w] = v;
+      }
+    }
     __syncthreads();
-    for (int l = warp; l < L; l += 4) {                                // hpmn.py:139
+    for (int l = warp; l < L; l += NT / 32) {                          // fc3 (40 -> 1), hpmn.py:139
       float s = 0.f;
-      for (int o = lane; o < ATT2; o += 32) s = fmaf(sZ2[l * ATT2 + o], __ldg(P + a.A3[hop] + o), s);
+      for (int o = lane; o < ATT2; o += 32) s = fmaf(S.Z2[l * ATT2 + o], S.A3[o], s);
       s = warp_sum(s);
       if (lane == 0) sS[l] = s + __ldg(P + a.a3[hop]);
     }
@@ -149,30 +174,30 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
       sQn[tid] = qn;
       a.ws.q[((int64_t)(hop + 1) * B + b) * H + tid] = qn;
     }
+    if (hop + 1 < a.hops) stage_weights(P, a, hop + 1, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
     __syncthreads();
     if (tid < H) sQ[tid] = sQn[tid];
     __syncthreads();
   }
   if (tid < H) a.repre[(int64_t)b * (H + D) + tid] = sQ[tid];         // concat([query, last]), hpmn.py:442
-  for (int e = tid; e < D; e += 128) a.repre[(int64_t)b * (H + D) + H + e] = sLast[e];
+  for (int e = tid; e < D; e += NT) a.repre[(int64_t)b * (H + D) + H + e] = sLast[e];
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NT)
 attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ __align__(16) float dsm[];
   __shared__ float sM[ML][HP];
   __shared__ float sDm[ML][HP];
   __shared__ float sT[ML][HP];
   __shared__ float sC[ML][ML];
-  __shared__ float sMean[ML], sRed[4], sW[ML], sDw[ML], sDs[ML], sMean2[ML];
+  __shared__ float sMean[ML], sRed[NT / 32], sW[ML], sDw[ML], sDs[ML], sMean2[ML];
   __shared__ float sLast[MD], sDlast[MD], sQ[HP], sDq[HP], sDqin[HP];
-  __shared__ float sDinp[ML * 4 * HP];
-  __shared__ float sZ1[ML * ATT1];       // holds z1, then dz1
-  __shared__ float sZ2[ML * ATT2];       // holds z2, then dz2
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
+  AttSmem S(dsm, H4);                       // S.Inp holds d(inp); S.Z1 / S.Z2 hold z then dz
   const float* P = a.params;
-  for (int e = tid; e < L * H; e += 128) { sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e); sDm[e / H][e % H] = 0.f; }
-  for (int e = tid; e < D; e += 128) {
+  for (int e = tid; e < L * H; e += NT) { sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e); sDm[e / H][e % H] = 0.f; }
+  for (int e = tid; e < D; e += NT) {
     sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
     sDlast[e] = __ldg(a.drepre + (int64_t)b * (H + D) + H + e);
   }
@@ -183,10 +208,11 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
   }
   __syncthreads();
   for (int hop = a.hops - 1; hop >= 0; --hop) {
+    stage_weights(P, a, hop, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
     if (tid < H) sQ[tid] = __ldg(a.ws.q + ((int64_t)hop * B + b) * H + tid);
     if (tid < L) sW[tid] = __ldg(a.ws.w + ((int64_t)hop * B + b) * L + tid);
-    for (int e = tid; e < L * ATT1; e += 128) sZ1[e] = __ldg(a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1 + e);
-    for (int e = tid; e < L * ATT2; e += 128) sZ2[e] = __ldg(a.ws.z2 + ((int64_t)hop * B + b) * L * ATT2 + e);
+    for (int e = tid; e < L * ATT1; e += NT) S.Z1[e] = __ldg(a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1 + e);
+    for (int e = tid; e < L * ATT2; e += NT) S.Z2[e] = __ldg(a.ws.z2 + ((int64_t)hop * B + b) * L * ATT2 + e);
     __syncthreads();
     // q_out = q_in @ Hmap + read ;  read = sum_l w_l m_l
     if (tid < H) {
@@ -194,7 +220,7 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
       for (int j = 0; j < H; ++j) s = fmaf(sDq[j], __ldg(P + a.Hmap + (int64_t)tid * H + j), s);
       sDqin[tid] = s;
     }
-    for (int l = warp; l < L; l += 4) {
+    for (int l = warp; l < L; l += NT / 32) {
       const float dq = lane < H ? sDq[lane] : 0.f;
       const float m = lane < H ? sM[l][lane] : 0.f;
       if (lane < H) sDm[l][lane] = fmaf(dq, sW[l], sDm[l][lane]);
@@ -213,54 +239,41 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     }
     __syncthreads();
     // dz2 = ds * A3 (z2 > 0)
-    for (int e = tid; e < L * ATT2; e += 128) {
+    for (int e = tid; e < L * ATT2; e += NT) {
       const int l = e / ATT2, o = e % ATT2;
-      const float v = sZ2[e] > 0.f ? sDs[l] * __ldg(P + a.A3[hop] + o) : 0.f;
-      sZ2[e] = v;
+      const float v = S.Z2[e] > 0.f ? sDs[l] * S.A3[o] : 0.f;
+      S.Z2[e] = v;
       a.ws.dz2[((int64_t)hop * B + b) * L * ATT2 + e] = v;
     }
     __syncthreads();
     // dz1[l][o] = (sum_o2 dz2[l][o2] A2[o][o2]) (z1 > 0)
-    if (tid < ATT1) {
-      const float* A2row = P + a.A2[hop] + (int64_t)tid * ATT2;
-      for (int l0 = 0; l0 < L; l0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int ll = 0; ll < 8; ++ll) acc[ll] = 0.f;
-        for (int o2 = 0; o2 < ATT2; ++o2) {
-          const float w = __ldg(A2row + o2);
-#pragma unroll
-          for (int ll = 0; ll < 8; ++ll)
-            if (l0 + ll < L) acc[ll] = fmaf(sZ2[(l0 + ll) * ATT2 + o2], w, acc[ll]);
-        }
-#pragma unroll
-        for (int ll = 0; ll < 8; ++ll)
-          if (l0 + ll < L) {
-            const int idx = (l0 + ll) * ATT1 + tid;
-            const float v = sZ1[idx] > 0.f ? acc[ll] : 0.f;
-            sZ1[idx] = v;                                              // own element only: no hazard
-            a.ws.dz1[((int64_t)hop * B + b) * L * ATT1 + idx] = v;
-          }
+    for (int w = tid; w < L * ATT1; w += NT) {
+      const int l = w / ATT1, o = w % ATT1;
+      const float* dz2 = S.Z2 + l * ATT2;
+      const float* row = S.A2 + o * A2S;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+      for (int o2 = 0; o2 < ATT2; o2 += 2) {
+        acc0 = fmaf(dz2[o2], row[o2], acc0);
+        acc1 = fmaf(dz2[o2 + 1], row[o2 + 1], acc1);
       }
+      const float v = S.Z1[w] > 0.f ? acc0 + acc1 : 0.f;
+      S.Z1[w] = v;                                                     // own element only: no hazard
+      a.ws.dz1[((int64_t)hop * B + b) * L * ATT1 + w] = v;
     }
     __syncthreads();
     // dinp[l][i] = sum_o dz1[l][o] A1[i][o]
-    if (tid < H4) {
-      const float* A1row = P + a.A1[hop] + (int64_t)tid * ATT1;
-      for (int l0 = 0; l0 < L; l0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int ll = 0; ll < 8; ++ll) acc[ll] = 0.f;
-        for (int o = 0; o < ATT1; ++o) {
-          const float w = __ldg(A1row + o);
-#pragma unroll
-          for (int ll = 0; ll < 8; ++ll)
-            if (l0 + ll < L) acc[ll] = fmaf(sZ1[(l0 + ll) * ATT1 + o], w, acc[ll]);
-        }
-#pragma unroll
-        for (int ll = 0; ll < 8; ++ll)
-          if (l0 + ll < L) sDinp[(l0 + ll) * H4 + tid] = acc[ll];
+    for (int w = tid; w < L * H4; w += NT) {
+      const int l = w / H4, i = w % H4;
+      const float* dz1 = S.Z1 + l * ATT1;
+      const float* row = S.A1 + i * A1S;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+      for (int o = 0; o < ATT1; o += 2) {
+        acc0 = fmaf(dz1[o], row[o], acc0);
+        acc1 = fmaf(dz1[o + 1], row[o + 1], acc1);
       }
+      S.Inp[l * H4 + i] = acc0 + acc1;
     }
     __syncthreads();
     // inp = [q, m, q-m, q*m]
@@ -268,8 +281,8 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
       const float q = sQ[tid];
       float dQ = 0.f;
       for (int l = 0; l < L; ++l) {
-        const float d0 = sDinp[l * H4 + tid], d1 = sDinp[l * H4 + H + tid], d2 = sDinp[l * H4 + 2 * H + tid],
-                    d3 = sDinp[l * H4 + 3 * H + tid];
+        const float d0 = S.Inp[l * H4 + tid], d1 = S.Inp[l * H4 + H + tid], d2 = S.Inp[l * H4 + 2 * H + tid],
+                    d3 = S.Inp[l * H4 + 3 * H + tid];
         const float m = sM[l][tid];
         dQ += d0 + d2 + d3 * m;
         sDm[l][tid] += d1 - d2 + d3 * q;
@@ -281,7 +294,7 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     __syncthreads();
   }
   // q0 = last @ Wq + bq
-  for (int i = tid; i < D; i += 128) {
+  for (int i = tid; i < D; i += NT) {
     float s = sDlast[i];
     for (int j = 0; j < H; ++j) s = fmaf(sDq[j], __ldg(P + a.Wq + (int64_t)i * H + j), s);
     a.dlast[(int64_t)b * D + i] = s;
@@ -289,7 +302,7 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
   // covreg adjoint: d||offdiag C||_F = C_off / ||.|| ;  C = mc mc^T / H ; mc = M - mean_j
   const float nrm = covreg_block(sM, sMean, sC, sRed, L, H);
   const float scale = nrm > 0.f ? a.memory_reg * 2.f / ((float)H * nrm) : 0.f;   // TF yields NaN at nrm == 0; we yield 0
-  for (int e = tid; e < L * H; e += 128) {
+  for (int e = tid; e < L * H; e += NT) {
     const int l = e / H, j = e % H;
     float s = 0.f;
     for (int l2 = 0; l2 < L; ++l2) s = fmaf(sC[l][l2], sM[l2][j] - sMean[l2], s);
@@ -302,7 +315,7 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     sMean2[tid] = s / (float)H;
   }
   __syncthreads();
-  for (int e = tid; e < L * H; e += 128) {
+  for (int e = tid; e < L * H; e += NT) {
     const int l = e / H, j = e % H;
     a.dmemory[(int64_t)b * L * H + e] = sDm[l][j] + sT[l][j] - sMean2[l];
   }
@@ -325,7 +338,9 @@ void launch_attn_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
                      cudaStream_t st) {
   AttnArgs a = make_args(d, pl, last_offset, memory, x, params, ws);
   a.repre = repre; a.w_hop0 = w_hop0; a.scalars = scalars;
-  attn_fwd_kernel<<<d.B, 128, 0, st>>>(a);
+  const size_t dsm = AttSmem::bytes(4 * d.H);
+  cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+  attn_fwd_kernel<<<d.B, NT, dsm, st>>>(a);
   ++*L.counter;
 }
 
@@ -334,7 +349,9 @@ void launch_attn_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
                      float* dlast, float* grads, const AttWs& ws, AtbBatch& batch, cudaStream_t st) {
   AttnArgs a = make_args(d, pl, last_offset, memory, x, params, ws);
   a.drepre = drepre; a.dmemory = dmemory; a.dlast = dlast; a.memory_reg = memory_reg;
-  attn_bwd_kernel<<<d.B, 128, 0, st>>>(a);
+  const size_t dsm = AttSmem::bytes(4 * d.H);
+  cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+  attn_bwd_kernel<<<d.B, NT, dsm, st>>>(a);
   ++*L.counter;
   // weight gradients: reductions over the batch, queued for one batched launch
   auto add = [&](const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int I, int N) {

@@ -295,6 +295,12 @@ void launch_pack(const Launch&, const Dims&, const ParamLayout&, const PackLayou
 // C[M,N] = A[M,K](row stride lda) * W[K,N] (+ bias[N]); N, K multiples of 4
 void launch_gemm_nn(const Launch&, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
                     int N, int K, cudaStream_t st);
+// same contract on tcgen05 tensor cores (3xTF32); returns false when (K,N) has no instantiation
+bool launch_tc_gemm_nn(const Launch&, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
+                       int N, int K, cudaStream_t st);
+// GRU weight gradients on tcgen05 (same contract as launch_gru_wgrad); false when the shape has no instantiation
+bool launch_tc_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* st, const float* da,
+                     float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_);
 // batched C[I,N](ldc) += sum_m A[m,I](lda) * Bm[m,N](ldb) with atomic accumulation; A == nullptr -> ones
 struct AtbProb {
   const float* A; const float* Bm; float* C;
@@ -325,10 +331,11 @@ void launch_attn_bwd(const Launch&, const Dims&, const ParamLayout&, int last_of
                      const float* x, const float* params, const float* drepre, float* dmemory, float* dlast, float* grads,
                      const AttWs& ws, AtbBatch& batch, cudaStream_t st);
 
-void launch_head_fwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, const float* repre,
+// row0: first batch row of this row group (keeps the dropout hash independent of how the batch is grouped)
+void launch_head_fwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, int row0, const float* repre,
                      const int32_t* labels, const float* params, float* pred, float* logit, float* scalars,
                      const HeadWs& ws, cudaStream_t st);
-void launch_head_bwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, const float* repre,
+void launch_head_bwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, int row0, const float* repre,
                      const int32_t* labels, const float* params, const float* pred, float* drepre, float* grads,
                      const HeadWs& ws, AtbBatch& batch, cudaStream_t st);
 

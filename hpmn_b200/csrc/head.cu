@@ -14,7 +14,7 @@ struct HeadArgs {
   const float* repre; const int32_t* labels; const float* params; const float* pred_in;
   float* pred; float* logit; float* scalars; float* drepre;
   HeadWs ws;
-  int B, R;
+  int B, R, row0;
   float keep_prob, inv_bn, inv_lossB;
   uint64_t seed;
   int64_t gamma, beta, F1, f1, F2, f2, F3, f3;
@@ -41,7 +41,7 @@ head_fwd_kernel(const __grid_constant__ HeadArgs a) {
     for (int i = 0; i < R; ++i) s = fmaf(sBn[i], __ldg(P + a.F1 + (int64_t)i * FC1 + tid), s);
     a.ws.a1[(int64_t)b * FC1 + tid] = s;
     float act = elu_f(s);
-    if (drop) act = dropout_keep(a.seed, 0, b, tid, a.keep_prob) ? act * inv_keep : 0.f;
+    if (drop) act = dropout_keep(a.seed, 0, a.row0 + b, tid, a.keep_prob) ? act * inv_keep : 0.f;
     sAct1[tid] = act;
     a.ws.act1[(int64_t)b * FC1 + tid] = act;
   }
@@ -51,7 +51,7 @@ head_fwd_kernel(const __grid_constant__ HeadArgs a) {
     for (int i = 0; i < FC1; ++i) s = fmaf(sAct1[i], __ldg(P + a.F2 + (int64_t)i * FC2 + tid), s);
     a.ws.a2[(int64_t)b * FC2 + tid] = s;
     float act = elu_f(s);
-    if (drop) act = dropout_keep(a.seed, 1, b, tid, a.keep_prob) ? act * inv_keep : 0.f;
+    if (drop) act = dropout_keep(a.seed, 1, a.row0 + b, tid, a.keep_prob) ? act * inv_keep : 0.f;
     sAct2[tid] = act;
     a.ws.act2[(int64_t)b * FC2 + tid] = act;
   }
@@ -90,7 +90,7 @@ head_bwd_kernel(const __grid_constant__ HeadArgs a) {
   __syncthreads();
   if (tid < FC2) {
     float d = sDlogit * __ldg(P + a.F3 + tid);
-    if (drop) d = dropout_keep(a.seed, 1, b, tid, a.keep_prob) ? d * inv_keep : 0.f;
+    if (drop) d = dropout_keep(a.seed, 1, a.row0 + b, tid, a.keep_prob) ? d * inv_keep : 0.f;
     d *= elu_grad_f(__ldg(a.ws.a2 + (int64_t)b * FC2 + tid));
     sDl2[tid] = d;
     a.ws.dl2[(int64_t)b * FC2 + tid] = d;
@@ -100,7 +100,7 @@ head_bwd_kernel(const __grid_constant__ HeadArgs a) {
     const float* row = P + a.F2 + (int64_t)tid * FC2;
     float d = 0.f;
     for (int o = 0; o < FC2; ++o) d = fmaf(sDl2[o], __ldg(row + o), d);
-    if (drop) d = dropout_keep(a.seed, 0, b, tid, a.keep_prob) ? d * inv_keep : 0.f;
+    if (drop) d = dropout_keep(a.seed, 0, a.row0 + b, tid, a.keep_prob) ? d * inv_keep : 0.f;
     d *= elu_grad_f(__ldg(a.ws.a1 + (int64_t)b * FC1 + tid));
     sDl1[tid] = d;
     a.ws.dl1[(int64_t)b * FC1 + tid] = d;
@@ -117,11 +117,11 @@ head_bwd_kernel(const __grid_constant__ HeadArgs a) {
   }
 }
 
-static HeadArgs make_args(const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, const float* repre,
+static HeadArgs make_args(const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, int row0, const float* repre,
                           const int32_t* labels, const float* params, const HeadWs& ws) {
   HeadArgs a; memset(&a, 0, sizeof(a));
   a.repre = repre; a.labels = labels; a.params = params; a.ws = ws;
-  a.B = d.B; a.R = d.R;
+  a.B = d.B; a.R = d.R; a.row0 = row0;
   a.keep_prob = hy.keep_prob > 0.f ? hy.keep_prob : 1.f;
   a.inv_bn = 1.0f / sqrtf(1.0f + BN_EPS);
   a.inv_lossB = 1.0f / (float)(hy.loss_batch > 0 ? hy.loss_batch : d.B);
@@ -130,19 +130,19 @@ static HeadArgs make_args(const Dims& d, const ParamLayout& pl, const hpmn_hyper
   return a;
 }
 
-void launch_head_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, const float* repre,
+void launch_head_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, int row0, const float* repre,
                      const int32_t* labels, const float* params, float* pred, float* logit, float* scalars,
                      const HeadWs& ws, cudaStream_t st) {
-  HeadArgs a = make_args(d, pl, hy, repre, labels, params, ws);
+  HeadArgs a = make_args(d, pl, hy, row0, repre, labels, params, ws);
   a.pred = pred; a.logit = logit; a.scalars = scalars;
   head_fwd_kernel<<<d.B, 256, 0, st>>>(a);
   ++*L.counter;
 }
 
-void launch_head_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, const float* repre,
+void launch_head_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, const hpmn_hyper& hy, int row0, const float* repre,
                      const int32_t* labels, const float* params, const float* pred, float* drepre, float* grads,
                      const HeadWs& ws, AtbBatch& batch, cudaStream_t st) {
-  HeadArgs a = make_args(d, pl, hy, repre, labels, params, ws);
+  HeadArgs a = make_args(d, pl, hy, row0, repre, labels, params, ws);
   a.pred_in = pred; a.drepre = drepre;
   head_bwd_kernel<<<d.B, 256, 0, st>>>(a);
   ++*L.counter;

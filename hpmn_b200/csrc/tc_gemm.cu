@@ -1,0 +1,428 @@
+// tc_gemm.cu -- the non-recurrent halves of the GRU gate GEMMs on the 5th-gen tensor cores.
+//
+//   C[M,N] = A[M,K] * W[K,N] (+ bias)       M = B*S_k rows (up to 262 144), K,N in {32,48,64,96}
+//
+// used for the input projections P = X*W_x + b (the x-half of the two _Linear calls of
+// /root/reference/code/util.py:88-107, hoisted out of the time loop) and for their adjoint dX = dA*W_x^T.
+//
+// tcgen05.mma kind::tf32, cta_group::1, M=128 rows per tile, accumulator in TMEM (128 lanes x N columns fp32),
+// issued by one thread, completion through tcgen05.commit -> mbarrier, read back with tcgen05.ld.
+// Precision: 3xTF32.  Each fp32 operand is split in registers into hi = rna_tf32(x), lo = rna_tf32(x - hi) and
+// D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo accumulates in fp32 -- ~2^-20 relative per product, which keeps the
+// 1e-4 parity budget through the recurrence that consumes P (single-pass tf32 would not).
+// Operands reach shared memory from registers (the split needs a register pass anyway) in the canonical
+// no-swizzle K-major core-matrix layout: 16-byte K-chunk c of row r lives at c*CHS + r*16, so a core matrix
+// (8 rows x 16 B) is 128 contiguous bytes, SBO = 128 B, LBO = CHS (padded by 16 B to spread banks).
+// The kernels are HBM-bound streams (A in, C out); several CTAs per SM overlap load / MMA / epilogue.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace hpmn {
+
+// ---- tcgen05 PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// shared-memory matrix descriptor, no swizzle (layout_type 0), sm_100 version bit set
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+// instruction descriptor: c=f32, a=b=tf32, K-major (0) or MN-major (1) operands, N>>3, M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int K, int N>
+__global__ void __launch_bounds__(128)
+tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ bias,
+                  float* __restrict__ C, int64_t M) {
+  constexpr int KC = K / 4;                       // 16-byte chunks along K
+  constexpr int CHS_A = 128 * 16 + 16;            // bytes between K-chunks of the A tile (padded)
+  constexpr int CHS_B = N * 16 + 16;
+  constexpr int TCOLS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, N, 0, 0);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sAhi = smem_raw;
+  unsigned char* sAlo = sAhi + KC * CHS_A;
+  unsigned char* sBhi = sAlo + KC * CHS_A;
+  unsigned char* sBlo = sBhi + KC * CHS_B;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBlo + KC * CHS_B);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(tslot, TCOLS);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  // weights: B[n][k] = W[k][n], split once per CTA
+  for (int e = tid; e < K * N; e += 128) {
+    const int k = e / N, n = e % N;
+    const float w = __ldg(W + e);
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    const int off = (k >> 2) * CHS_B + n * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(sBhi + off) = hi;
+    *reinterpret_cast<float*>(sBlo + off) = lo;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  const int64_t tiles = (M + 127) / 128;
+  float4 areg[KC];                                // this thread's 16-byte chunks of the current tile
+  auto load_tile = [&](int64_t tile) {
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      const int e = tid + 128 * i;
+      const int row = e / KC, c = e % KC;
+      const int64_t m = tile * 128 + row;
+      areg[i] = m < M ? ldg_nc_f4(reinterpret_cast<const float4*>(A + m * lda) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < tiles) load_tile(tile);
+  uint32_t phase = 0;
+  for (; tile < tiles; tile += gridDim.x) {
+    // registers -> (hi, lo) -> shared, canonical K-major layout
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      const int e = tid + 128 * i;
+      const int row = e / KC, c = e % KC;
+      const float4 v = areg[i];
+      float4 hi, lo;
+      hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+      lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+      *reinterpret_cast<float4*>(sAhi + c * CHS_A + row * 16) = hi;
+      *reinterpret_cast<float4*>(sAlo + c * CHS_A + row * 16) = lo;
+    }
+    fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(sAhi), al = smem_u32(sAlo), bh = smem_u32(sBhi), bl = smem_u32(sBlo);
+#pragma unroll
+      for (int s = 0; s < K / 8; ++s) {
+        const uint64_t dah = umma_desc(ah + s * 2 * CHS_A, CHS_A, 128), dal = umma_desc(al + s * 2 * CHS_A, CHS_A, 128);
+        const uint64_t dbh = umma_desc(bh + s * 2 * CHS_B, CHS_B, 128), dbl = umma_desc(bl + s * 2 * CHS_B, CHS_B, 128);
+        tc_mma_tf32(tmem, dah, dbh, IDESC, s > 0);
+        tc_mma_tf32(tmem, dal, dbh, IDESC, 1);
+        tc_mma_tf32(tmem, dah, dbl, IDESC, 1);
+      }
+      tc_commit(bar);                             // arrives when every MMA above has finished reading smem / writing TMEM
+    }
+    const int64_t next = tile + gridDim.x;
+    if (next < tiles) load_tile(next);            // next tile's global loads fly during the MMA and the epilogue
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // epilogue: TMEM lane = row, 16 columns per load
+    const int64_t m = tile * 128 + warp * 32 + lane;
+#pragma unroll
+    for (int cb = 0; cb < N / 16; ++cb) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb * 16, v);
+      if (m < M) {
+        float4* dst = reinterpret_cast<float4*>(C + m * N + cb * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (bias != nullptr) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + cb * 16) + q);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+          }
+          dst[q] = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                              // TMEM drained and smem free before the next tile's writes / MMAs
+  }
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GRU weight gradients on tensor cores:  D[I,N] = sum_m At[m,I] * dA[m,N]   (reduction over all B*S_k rows)
+//   I (MMA M = 128) = [x (DINP) | h_prev (32) | r*h_prev (32) | zero pad ... | ones]   N = 96 = da_r | da_u | da_c
+//   dWg = rows {x,h} x cols {r,u};  dWc = rows {x,r*h} x cols {c};  the ones row (I = 127) yields the bias gradients.
+// The reduction dimension (rows of global memory) is the MMA K dimension, so both operands are transposed on the
+// way into shared memory: element (feature i, row k) lives at (k/4)*CHS + i*16 + (k%4)*4 -- the same K-major
+// core-matrix layout as tc_gemm_nn (kind::tf32 with MN-major descriptors returned zeros on this part, so the
+// transpose is done by the producers: lanes map to rows, and because CHS = 16 mod 128 bytes the 32 scalar stores of
+// a warp hit 32 different banks).
+// Warp-specialised: 4 producer warps (global -> registers -> hi/lo split, r*h -> shared, 3 stages of 32 rows),
+// 1 MMA warp (single issuing thread, 3xTF32); the accumulator stays in TMEM for the CTA's whole row range and is
+// scattered into the TF weight layout once at the end.
+// ---------------------------------------------------------------------------------------------------
+constexpr int WK = 32;                 // rows per stage (= MMA K per stage)
+constexpr int WNS = 3;                 // stages
+constexpr int WCHS_A = 128 * 16 + 16;  // bytes between 4-row K chunks of the feature tile (padded)
+constexpr int WCHS_B = 96 * 16 + 16;
+constexpr int W_AT = (WK / 4) * WCHS_A;
+constexpr int W_B = (WK / 4) * WCHS_B;
+constexpr int W_STAGE = 2 * W_AT + 2 * W_B;
+
+// scatter 4 consecutive features of row k (hi and lo parts) into a K-major tile
+__device__ __forceinline__ void put_t(unsigned char* hi_base, unsigned char* lo_base, int chs, int feat0, int k, float4 v) {
+  const int off = (k >> 2) * chs + feat0 * 16 + (k & 3) * 4;
+  const float hx = tf32_rna(v.x), hy = tf32_rna(v.y), hz = tf32_rna(v.z), hw = tf32_rna(v.w);
+  *reinterpret_cast<float*>(hi_base + off) = hx;
+  *reinterpret_cast<float*>(hi_base + off + 16) = hy;
+  *reinterpret_cast<float*>(hi_base + off + 32) = hz;
+  *reinterpret_cast<float*>(hi_base + off + 48) = hw;
+  *reinterpret_cast<float*>(lo_base + off) = tf32_rna(v.x - hx);
+  *reinterpret_cast<float*>(lo_base + off + 16) = tf32_rna(v.y - hy);
+  *reinterpret_cast<float*>(lo_base + off + 32) = tf32_rna(v.z - hz);
+  *reinterpret_cast<float*>(lo_base + off + 48) = tf32_rna(v.w - hw);
+}
+
+constexpr int WPW = 8;                 // producer warps (2 per SM sub-partition: the convert/transposing stores are issue-bound)
+
+template <int DINP>
+__global__ void __launch_bounds__(32 * (WPW + 1))
+tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restrict__ st, const float* __restrict__ da,
+                float* __restrict__ dWg, float* __restrict__ dbg, float* __restrict__ dWc, float* __restrict__ dbc, int64_t M,
+                int S, int Din, int H, int64_t rows_per_cta) {
+  static_assert(DINP + 64 < 128, "the ones row needs a free feature slot");
+  constexpr int XC = DINP / 4;           // feature chunks of x
+  constexpr int NXU = XC;                // work units (16 rows x 2 chunks) in the x part
+  constexpr int NX = (NXU + WPW - 1) / WPW;
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, 96, 0, 0);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + WNS * W_STAGE);
+  uint64_t* empty = full + WNS;
+  uint64_t* done = empty + WNS;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t mbeg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t mend = mbeg + rows_per_cta < M ? mbeg + rows_per_cta : M;
+  const int nst = mend > mbeg ? (int)((mend - mbeg + WK - 1) / WK) : 0;
+
+  if (warp == WPW) tmem_alloc(tslot, 128);
+  if (tid == 0) {
+    for (int i = 0; i < WNS; ++i) { mbar_init(&full[i], 32 * WPW); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  // pad features [DINP+64, 128): zeros, except feature 127 = 1.0 (hi part) -> bias gradients
+  for (int e = tid; e < WNS * (64 - DINP) * WK; e += 32 * (WPW + 1)) {
+    const int stg = e / ((64 - DINP) * WK), r = e % ((64 - DINP) * WK);
+    const int feat = DINP + 64 + r / WK, k = r % WK;
+    unsigned char* base = smem_raw + stg * W_STAGE;
+    const int off = (k >> 2) * WCHS_A + feat * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(base + off) = feat == 127 ? 1.f : 0.f;   // hi
+    *reinterpret_cast<float*>(base + W_AT + off) = 0.f;                // lo
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp < WPW) {
+    // ================= producers =================
+    // two register buffers: the global loads of stage s+2 are in flight while stage s+1 is converted and stored
+    struct Regs { float4 x[NX], h[1], r[1], d[3]; };
+    Regs bufA, bufB;
+    // work unit u = warp + 4*i covers 16 rows x 2 adjacent 16-byte chunks: every 32-byte sector a warp touches is
+    // used completely (no reliance on L1 hits), and the 32 scalar stores of put_t land in 32 different banks
+    const int lk = lane >> 1, lc = lane & 1;
+    auto load = [&](Regs& R, int sidx) {
+      const int64_t m0 = mbeg + (int64_t)sidx * WK;
+      const bool live = sidx < nst;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
+        const int64_t m = m0 + 16 * (u & 1) + lk;
+        R.x[i] = (live && u < NXU && m < mend) ? __ldg(reinterpret_cast<const float4*>(xin + m * ldx) + c) : z;
+      }
+#pragma unroll
+      for (int i = 0; i < 1; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
+        const int64_t m = m0 + 16 * (u & 1) + lk;
+        const bool ok = live && m < mend;
+        R.h[i] = (ok && m % S != 0) ? __ldg(reinterpret_cast<const float4*>(st + (m - 1) * ST) + c) : z;
+        R.r[i] = ok ? __ldg(reinterpret_cast<const float4*>(st + m * ST + HP) + c) : z;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
+        const int64_t m = m0 + 16 * (u & 1) + lk;
+        R.d[i] = (live && m < mend) ? __ldg(reinterpret_cast<const float4*>(da + m * G3) + c) : z;
+      }
+    };
+    auto store = [&](const Regs& R, int sidx) {
+      const int slot = sidx % WNS;
+      if (sidx >= WNS) mbar_wait(&empty[slot], (uint32_t)((sidx / WNS) - 1) & 1u);     // MMAs that read this slot are done
+      unsigned char* base = smem_raw + slot * W_STAGE;
+      unsigned char* At_hi = base;
+      unsigned char* At_lo = base + W_AT;
+      unsigned char* B_hi = base + 2 * W_AT;
+      unsigned char* B_lo = base + 2 * W_AT + W_B;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc, k = 16 * (u & 1) + lk;
+        if (u < NXU) put_t(At_hi, At_lo, WCHS_A, 4 * c, k, R.x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 1; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc, k = 16 * (u & 1) + lk;
+        put_t(At_hi, At_lo, WCHS_A, DINP + 4 * c, k, R.h[i]);
+        put_t(At_hi, At_lo, WCHS_A, DINP + 32 + 4 * c, k,
+              make_float4(R.h[i].x * R.r[i].x, R.h[i].y * R.r[i].y, R.h[i].z * R.r[i].z, R.h[i].w * R.r[i].w));
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc, k = 16 * (u & 1) + lk;
+        put_t(B_hi, B_lo, WCHS_B, 4 * c, k, R.d[i]);
+      }
+      fence_proxy_async();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+    };
+    load(bufA, 0);
+    load(bufB, 1);
+    for (int sidx = 0; sidx < nst; sidx += 2) {
+      store(bufA, sidx);
+      load(bufA, sidx + 2);
+      if (sidx + 1 < nst) {
+        store(bufB, sidx + 1);
+        load(bufB, sidx + 3);
+      }
+    }
+    // ================= epilogue (warps 0-3): TMEM lane = input feature =================
+    if (warp < 4) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int i = warp * 32 + lane;
+    int kind, row;                       // kind 0: x row, 1: h row (gates only), 2: r*h row (candidate only), 3: bias, -1: pad
+    if (i < DINP) { kind = i < Din ? 0 : -1; row = i; }
+    else if (i < DINP + 32) { kind = (i - DINP) < H ? 1 : -1; row = Din + (i - DINP); }
+    else if (i < DINP + 64) { kind = (i - DINP - 32) < H ? 2 : -1; row = Din + (i - DINP - 32); }
+    else { kind = i == 127 ? 3 : -1; row = 0; }
+#pragma unroll
+    for (int cb = 0; cb < 6; ++cb) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb * 16, v);
+      if (nst == 0 || kind < 0) continue;
+      const int g = cb >> 1;             // 0: r, 1: u, 2: c
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int j = (cb & 1) * 16 + q;
+        if (j >= H) continue;
+        if (kind == 3) {
+          if (g < 2) atomicAdd(dbg + g * H + j, v[q]); else atomicAdd(dbc + j, v[q]);
+        } else if (g < 2) {
+          if (kind != 2) atomicAdd(dWg + (int64_t)row * 2 * H + g * H + j, v[q]);
+        } else {
+          if (kind != 1) atomicAdd(dWc + (int64_t)row * H + j, v[q]);
+        }
+      }
+    }
+    tc_fence_before();
+    }
+  } else {
+    // ================= MMA warp =================
+    if (lane == 0) {
+      for (int sidx = 0; sidx < nst; ++sidx) {
+        const int slot = sidx % WNS;
+        mbar_wait(&full[slot], (uint32_t)(sidx / WNS) & 1u);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem_raw + slot * W_STAGE);
+        const uint32_t ah = base, al = base + W_AT, bh = base + 2 * W_AT, bl = base + 2 * W_AT + W_B;
+#pragma unroll
+        for (int ks = 0; ks < WK / 8; ++ks) {
+          const uint64_t dah = umma_desc(ah + ks * 2 * WCHS_A, WCHS_A, 128), dal = umma_desc(al + ks * 2 * WCHS_A, WCHS_A, 128);
+          const uint64_t dbh = umma_desc(bh + ks * 2 * WCHS_B, WCHS_B, 128), dbl = umma_desc(bl + ks * 2 * WCHS_B, WCHS_B, 128);
+          tc_mma_tf32(tmem, dah, dbh, IDESC, (sidx | ks) != 0);
+          tc_mma_tf32(tmem, dal, dbh, IDESC, 1);
+          tc_mma_tf32(tmem, dah, dbl, IDESC, 1);
+        }
+        tc_commit(&empty[slot]);
+      }
+      tc_commit(done);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == WPW) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+bool launch_tc_wgrad(const Launch& L, const Dims& d, int k, const float* xin, int64_t ldx, const float* st, const float* da,
+                     float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_) {
+  const int DinP = d.DinP[k];
+  if (DinP != 32 && DinP != 48) return false;
+  const int64_t M = (int64_t)d.B * d.S[k];
+  const size_t smem = (size_t)WNS * W_STAGE + 128;
+  int64_t stages = (M + WK - 1) / WK;
+  int64_t ctas = stages / 8 < L.sms ? stages / 8 : L.sms;      // >= 8 stages per CTA: every CTA ends with ~12 k atomics
+  if (ctas < 1) ctas = 1;
+  const int64_t rpc = ((stages + ctas - 1) / ctas) * WK;
+  ctas = (M + rpc - 1) / rpc;
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)ctas, 32 * (WPW + 1), smem, st_>>>(xin, ldx, st, da, dWg, dbg, dWc, dbc, M, d.S[k], d.Din[k], d.H, rpc);
+  };
+  if (DinP == 32) go(tc_wgrad_kernel<32>); else go(tc_wgrad_kernel<48>);
+  ++*L.counter;
+  return true;
+}
+
+template <int K, int N>
+static void launch_one(const Launch& L, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
+                       cudaStream_t st) {
+  constexpr int KC = K / 4;
+  const size_t smem = (size_t)2 * KC * (128 * 16 + 16) + (size_t)2 * KC * (N * 16 + 16) + 64;
+  auto kern = tc_gemm_nn_kernel<K, N>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t tiles = (M + 127) / 128;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));   // resident CTAs: shared memory, then the 512-column TMEM budget
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)(tiles < (int64_t)L.sms * per_sm ? tiles : (int64_t)L.sms * per_sm);
+  kern<<<grid, 128, smem, st>>>(A, lda, W, bias, C, M);
+  ++*L.counter;
+}
+
+bool launch_tc_gemm_nn(const Launch& L, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
+                       int N, int K, cudaStream_t st) {
+#define HPMN_TC_CASE(KK, NN) if (K == KK && N == NN) { launch_one<KK, NN>(L, A, lda, W, bias, C, M, st); return true; }
+  HPMN_TC_CASE(32, 96) HPMN_TC_CASE(48, 96) HPMN_TC_CASE(64, 96)
+  HPMN_TC_CASE(96, 32) HPMN_TC_CASE(96, 48) HPMN_TC_CASE(96, 64)
+#undef HPMN_TC_CASE
+  return false;
+}
+
+}  // namespace hpmn

@@ -167,6 +167,13 @@ int hpmn_profile_enable(hpmn_ctx*, int on);
 int hpmn_profile_read(hpmn_ctx*, float* ms, int64_t* calls);
 const char* hpmn_kernel_family_name(int family);
 
+/* ---- kernel-level test hook ------------------------------------------------------------------ */
+/* GRU weight gradients of layer k from caller buffers: xin rows [B*S_k] (row stride ldx floats), st [B*S_k,128]
+ * (h|r|u|c), da [B*S_k,96]; accumulates into grads (flat layout).  use_tc: 1 = tcgen05 kernel, 0 = fp32 FFMA kernel.
+ * Returns HPMN_EINVAL if the requested implementation does not cover the shape. */
+int hpmn_debug_wgrad(hpmn_ctx*, const hpmn_shape*, int k, const float* xin, int64_t ldx, const float* st, const float* da,
+                     float* grads, int use_tc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
