@@ -14,6 +14,7 @@ using namespace hpmn;
 #define HPMN_MAX_GROUPS 4
 
 struct hpmn_ctx {
+  bool use_wave;    // fused wavefront kernels for the recurrence (HPMN_NO_WAVE=1 selects the layer-by-layer kernels)
   bool use_tc;      // tcgen05 path for the dense (non-recurrent) GEMMs; HPMN_NO_TC=1 selects the FFMA kernels
   int device;
   int sms;
@@ -184,6 +185,15 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
   { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
+  if (ctx->use_wave && d.L <= 11) {
+    // layer-0 input projections (dense, tensor cores), then every layer of every sample as one wavefront kernel
+    { Bracket b(ctx, st, HPMN_K_INPROJ);
+      dense_gemm(ctx, L, x, d.D, pw + p.pk.Wx[0], pw + p.pk.bx[0], p.f(p.wl.proj[0]), (int64_t)d.B * d.S[0], G3, d.DinP[0], st); }
+    float* stp[HPMN_MAX_LAYERS];
+    for (int k = 0; k < d.L; ++k) stp[k] = p.f(p.wl.st[k]);
+    Bracket b(ctx, st, HPMN_K_REC_FWD);
+    if (launch_wave_fwd(L, d, p.pk, p.f(p.wl.proj[0]), pw, stp, memory, st)) return;
+  }
   for (int k = 0; k < d.L; ++k) {
     const float* A = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;   // every p-th h row
     const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
@@ -255,6 +265,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx->device = device; ctx->sms = prop.multiProcessorCount; ctx->launches = 0; ctx->err[0] = 0;
   ctx->profile = false; ctx->pool_used = 0;
   { const char* e_tc = getenv("HPMN_NO_TC"); ctx->use_tc = !(e_tc && e_tc[0] == '1'); }
+  { const char* e_w = getenv("HPMN_NO_WAVE"); ctx->use_wave = !(e_w && e_w[0] == '1'); }
   memset(ctx->ms, 0, sizeof(ctx->ms)); memset(ctx->calls, 0, sizeof(ctx->calls));
   cudaSetDevice(device);
   e = cudaMalloc(&ctx->scratch, 256);

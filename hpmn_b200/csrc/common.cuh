@@ -320,6 +320,10 @@ void launch_rec_bwd(const Launch&, const Dims&, int k, const float* st, const fl
 void launch_gru_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* st, const float* da,
                       float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_);
 
+// all layers of the memory as one wavefront kernel (wave.cu); proj0 = layer-0 input projections; false if L is too large
+bool launch_wave_fwd(const Launch&, const Dims&, const PackLayout&, const float* proj0, const float* pw, float* const* st,
+                     float* memory, cudaStream_t st_);
+
 // resolved workspace pointers handed to the attention / head kernels
 struct AttWs { float *q, *dq, *w, *ds, *inp, *z1, *dz1, *z2, *dz2; };
 struct HeadWs { float *bn, *dbn, *dgt, *a1, *act1, *dl1, *a2, *act2, *dl2, *dlogit; };

@@ -10,7 +10,8 @@ from hpmn_b200.engine import HpmnEngine
 from hpmn_b200.layout import HpmnShape
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-sh = HpmnShape(B=B, T=1001, F=2, E=16, H=32, periods=[2, 2, 2, 2], L=5, hops=3, V=3308019, front_pad=23,
+NL = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+sh = HpmnShape(B=B, T=1001, F=2, E=16, H=32, periods=[2] * (NL - 1), L=NL, hops=3, V=3308019, front_pad=23,
                mask_id0=False, last_offset=2)
 eng = HpmnEngine(sh, memory_reg=5e-5)
 rng = np.random.default_rng(0)
