@@ -185,7 +185,7 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
   { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
-  if (ctx->use_wave && d.L <= 11) {
+  if (ctx->use_wave && d.L <= 10) {
     // layer-0 input projections (dense, tensor cores), then every layer of every sample as one wavefront kernel
     { Bracket b(ctx, st, HPMN_K_INPROJ);
       dense_gemm(ctx, L, x, d.D, pw + p.pk.Wx[0], pw + p.pk.bx[0], p.f(p.wl.proj[0]), (int64_t)d.B * d.S[0], G3, d.DinP[0], st); }
@@ -211,6 +211,33 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
+  if (ctx->use_wave && d.L <= 10) {
+    // every layer's reverse-time recurrence as one wavefront kernel (dx of layers >= 1 handed down in-kernel); then the
+    // dense work: layer-0 dX (feeds the embedding scatter) on `st`, all weight-gradient reductions on the side stream
+    const float* stp[HPMN_MAX_LAYERS]; float* dap[HPMN_MAX_LAYERS];
+    for (int k = 0; k < d.L; ++k) { stp[k] = p.f(p.wl.st[k]); dap[k] = p.f(p.wl.proj[k]); }
+    bool done;
+    { Bracket b(ctx, st, HPMN_K_REC_BWD);
+      done = launch_wave_bwd(L, d, p.pk, pw, stp, dap, dmemory, st); }
+    if (done) {
+      cudaStream_t ws = st;
+      if (ov) { cudaEventRecord(ctx->ev_fork[0], st); cudaStreamWaitEvent(ctx->side, ctx->ev_fork[0], 0); ws = ctx->side; }
+      { Bracket b(ctx, st, HPMN_K_WGRAD);
+        for (int k = 0; k < d.L; ++k) {
+          const float* A = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;
+          const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
+          float* da = dap[k];
+          if (!(ctx->use_tc && launch_tc_wgrad(L, d, k, A, lda, p.f(p.wl.st[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
+                                               grads + p.pl.Wc[k], grads + p.pl.bc[k], ws)))
+            launch_gru_wgrad(L, d, k, A, lda, p.f(p.wl.st[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
+                             grads + p.pl.Wc[k], grads + p.pl.bc[k], ws);
+        } }
+      { Bracket b(ctx, st, HPMN_K_DX);
+        dense_gemm(ctx, L, dap[0], G3, pw + p.pk.WxT[0], nullptr, dx0, (int64_t)d.B * d.S[0], d.DinP[0], G3, st); }
+      if (ov) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }
+      return;
+    }
+  }
   for (int k = d.L - 1; k >= 0; --k) {
     float* da = p.f(p.wl.proj[k]);
     const float* dx_up = k < d.L - 1 ? p.f(p.wl.dxk[k + 1]) : nullptr;

@@ -324,6 +324,10 @@ void launch_gru_wgrad(const Launch&, const Dims&, int k, const float* xin, int64
 bool launch_wave_fwd(const Launch&, const Dims&, const PackLayout&, const float* proj0, const float* pw, float* const* st,
                      float* memory, cudaStream_t st_);
 
+// backward twin: consumes st[k], dmemory; emits da[k] for every layer (dx of layers >= 1 is handed down in-kernel)
+bool launch_wave_bwd(const Launch&, const Dims&, const PackLayout&, const float* pw, const float* const* st, float* const* da,
+                     const float* dmemory, cudaStream_t st_);
+
 // resolved workspace pointers handed to the attention / head kernels
 struct AttWs { float *q, *dq, *w, *ds, *inp, *z1, *dz1, *z2, *dz2; };
 struct HeadWs { float *bn, *dbn, *dgt, *a1, *act1, *dl1, *a2, *act2, *dl2, *dlogit; };

@@ -11,6 +11,8 @@
 // receives the every-p-th hidden state of layer k-1 through a small shared-memory ring (producer / consumer counters)
 // and applies its own input projection with W_x read from shared memory -- upper layers step at most every other
 // layer-0 step, so they have the issue slots to spare.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hpmn {
@@ -19,7 +21,7 @@ constexpr int WCH = 8;        // steps per output chunk (one 4 KB bulk store)
 constexpr int WIN = 16;       // steps per input chunk of layer 0
 constexpr int WNS0 = 3;       // input ring stages of layer 0
 constexpr int HRS = 8;        // hand-off ring slots between consecutive layers
-constexpr int WAVE_MAX_L = 11;
+constexpr int WAVE_MAX_L = 10;
 
 struct WaveArgs {
   const float* proj0;              // [B,S_0,96]
@@ -195,7 +197,7 @@ __device__ __forceinline__ float wave_layer(const WaveArgs& a, int k, int b, int
   return h;
 }
 
-__global__ void __launch_bounds__(352)
+__global__ void __launch_bounds__(320)
 wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   const int tid = threadIdx.x, w = tid >> 5, j = tid & 31;
@@ -259,6 +261,237 @@ bool launch_wave_fwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   cudaFuncSetAttribute(wave_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
   const int grid = (d.B + nspc - 1) / nspc;
   wave_fwd_kernel<<<grid, 32 * d.L * nspc, sm.total, st_>>>(a);
+  { cudaError_t e = cudaGetLastError();                  // resources: the caller falls back to the per-layer kernels
+    if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_fwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * d.L * nspc, sm.total); return false; } }
+  ++*L.counter;
+  return true;
+}
+
+// =====================================================================================================
+// Backward wavefront: every layer walks its steps in reverse concurrently.  Layer k needs, at each of its firing
+// steps s = (j+1)*p_k - 1, the gradient dx_{k+1}[j] = da_{k+1}[j] * W_x^{(k+1)T} of the layer above; the warp of
+// layer k+1 computes it right after its step j (da_r|da_u|da_c are already broadcast in shared memory for the
+// recurrent dot products; W_x^T comes from shared memory) and hands it down through an mbarrier ring.  Saved state
+// rows stream in with cp.async.bulk (chunk = CHB steps needs rows s0-1 .. s0+len-1), da rows leave with bulk stores
+// for the weight-gradient kernel and, for layer 0, the dX GEMM that feeds the embedding scatter.
+// =====================================================================================================
+constexpr int BCH0 = 8, BNS0 = 3;   // layer 0: steps per chunk, state ring stages
+constexpr int BCHK = 4, BNSK = 2;   // layers >= 1 (not on the critical path): smaller rings
+
+struct WaveBwdArgs {
+  const float* pw;
+  const float* st[HPMN_MAX_LAYERS];   // [B,S_k,128]
+  float* da[HPMN_MAX_LAYERS];         // [B,S_k,96]
+  const float* dmemory;               // [B,L,H]
+  int64_t WhT[HPMN_MAX_LAYERS], WxT[HPMN_MAX_LAYERS];   // offsets into pw: WhT [3][32 j][32 i], WxT [96][32]
+  int S[HPMN_MAX_LAYERS], P[HPMN_MAX_LAYERS];
+  int B, L, H, nspc;
+};
+
+__host__ __device__ constexpr int bwd_region_bytes(int ch, int ns) {
+  return ns * (ch + 1) * ST * 4 + 2 * ch * G3 * 4 + 3 * 128 + 128;   // state ring | da ring | sh_c,sh_r,sh_u | mbarriers
+}
+
+struct WaveBwdSmem {
+  int wxt, hand, l0, lk, total;
+  __host__ __device__ WaveBwdSmem(int L, int nspc) {
+    int off = 0;
+    wxt = off; off += (L - 1) * 48 * HP * 8;               // float2 [q (48 pairs of n)][i] per layer >= 1
+    off = (off + 127) & ~127;
+    hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
+    off = (off + 127) & ~127;
+    l0 = off; off += nspc * bwd_region_bytes(BCH0, BNS0);
+    lk = off; off += (L - 1) * nspc * bwd_region_bytes(BCHK, BNSK);
+    total = off;
+  }
+};
+
+template <int CH, int NS>
+__device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int b, int i, unsigned char* reg, Handoff* hin,
+                                               Handoff* hout, const float2* myWxT) {
+  const int S = a.S[k], H = a.H, L = a.L;
+  const int period = k < L - 1 ? a.P[k] : 1;             // firing period towards layer k+1
+  float* s_st = reinterpret_cast<float*>(reg);           // [NS][(CH+1)*ST]
+  float* s_da = s_st + NS * (CH + 1) * ST;               // [2][CH*G3]
+  float* sh_c = s_da + 2 * CH * G3;
+  float* sh_r = sh_c + 32;
+  float* sh_u = sh_r + 32;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sh_u + 32);
+
+  float2 wrT[16], wuT[16], wcT[16];                      // lane i: W[Din+i][g*H + j] over j, natural (2q, 2q+1) pairs
+  {
+    const float* WhT = a.pw + a.WhT[k];                  // [3][32 j][32 i]
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      wrT[q] = make_float2(__ldg(WhT + (0 * HP + 2 * q) * HP + i), __ldg(WhT + (0 * HP + 2 * q + 1) * HP + i));
+      wuT[q] = make_float2(__ldg(WhT + (1 * HP + 2 * q) * HP + i), __ldg(WhT + (1 * HP + 2 * q + 1) * HP + i));
+      wcT[q] = make_float2(__ldg(WhT + (2 * HP + 2 * q) * HP + i), __ldg(WhT + (2 * HP + 2 * q + 1) * HP + i));
+    }
+  }
+  const float* sb = a.st[k] + (int64_t)b * S * ST;
+  float* dab = a.da[k] + (int64_t)b * S * G3;
+  const int nch = (S + CH - 1) / CH;
+
+  auto issue = [&](int ci, int stage) {                  // lane 0: load state rows s0-1 .. s0+len-1 of chunk ci
+    const int s0 = ci * CH;
+    const int len = min(CH, S - s0);
+    const uint32_t rows = (uint32_t)(s0 > 0 ? len + 1 : len);
+    mbar_expect_tx(&full[stage], rows * ST * 4);
+    if (s0 > 0) bulk_g2s(s_st + stage * (CH + 1) * ST, sb + (int64_t)(s0 - 1) * ST, rows * ST * 4, &full[stage]);
+    else bulk_g2s(s_st + stage * (CH + 1) * ST + ST, sb, rows * ST * 4, &full[stage]);    // buffer row t+1 <-> step s0+t
+  };
+  if (i == 0) {
+    for (int q = 0; q < NS; ++q) mbar_init(&full[q], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (i == 0)
+    for (int it = 0; it < NS && it < nch; ++it) issue(nch - 1 - it, it);
+
+  float dh_next = i < H ? __ldg(a.dmemory + ((int64_t)b * L + k) * H + i) : 0.f;   // memory-slot gradient enters at the last step
+  unsigned got = 0, sent = 0;                            // hand-offs consumed / produced
+  int to_fire = 1;                                       // the last step is a firing step: S % p == 0
+
+  auto step = [&](const float* ib, float* orow, bool first_step) {
+    const float hp = first_step ? 0.f : ib[i];           // h_{s-1}: state row s-1 (zero state before step 0)
+    const float r = ib[ST + HP + i], u = ib[ST + 2 * HP + i], c = ib[ST + 3 * HP + i];
+    float dh = dh_next;
+    if (hin != nullptr && --to_fire == 0) {              // this step fed layer k+1 in the forward pass
+      to_fire = period;
+      const int slot = got & (HRS - 1);
+      mbar_wait(&hin->full[slot], (got / HRS) & 1u);
+      dh += hin->ring[slot][i];
+      ++got;
+      __syncwarp();
+      if (i == 0) mbar_arrive(&hin->empty[slot]);
+    }
+    const float dc = dh * (1.f - u);
+    const float du = dh * (hp - c);
+    float dhp = dh * u;
+    const float dac = dc * (1.f - c * c);
+    sh_c[i] = dac;
+    __syncwarp();
+    const float drh = dotn(sh_c, wcT, 0.f);              // (da_c * Wc^T)[Din + i]
+    const float dr = drh * hp;
+    dhp = fmaf(drh, r, dhp);
+    const float dar = dr * r * (1.f - r);
+    const float dau = du * u * (1.f - u);
+    sh_r[i] = dar;
+    sh_u[i] = dau;
+    __syncwarp();
+    const float dhg = dotn(sh_r, wrT, 0.f) + dotn(sh_u, wuT, 0.f);   // (da_g * Wg^T)[Din + i]
+    dh_next = dhp + dhg;
+    orow[i] = dar;
+    orow[HP + i] = dau;
+    orow[2 * HP + i] = dac;
+    if (hout != nullptr) {                               // dx of this step -> layer k-1 (every step of layer k is one of its firing steps)
+      float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0;
+      const float4* r4 = reinterpret_cast<const float4*>(sh_r);
+      const float4* u4 = reinterpret_cast<const float4*>(sh_u);
+      const float4* c4 = reinterpret_cast<const float4*>(sh_c);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 vr = r4[q4], vu = u4[q4], vc = c4[q4];
+        x0 = ffma2(make_float2(vr.x, vr.y), myWxT[(2 * q4) * HP + i], x0);
+        x0 = ffma2(make_float2(vr.z, vr.w), myWxT[(2 * q4 + 1) * HP + i], x0);
+        x1 = ffma2(make_float2(vu.x, vu.y), myWxT[(16 + 2 * q4) * HP + i], x1);
+        x1 = ffma2(make_float2(vu.z, vu.w), myWxT[(16 + 2 * q4 + 1) * HP + i], x1);
+        x2 = ffma2(make_float2(vc.x, vc.y), myWxT[(32 + 2 * q4) * HP + i], x2);
+        x2 = ffma2(make_float2(vc.z, vc.w), myWxT[(32 + 2 * q4 + 1) * HP + i], x2);
+      }
+      const float dx = (x0.x + x0.y) + (x1.x + x1.y) + (x2.x + x2.y);
+      const int slot = sent & (HRS - 1);
+      if (sent >= HRS) mbar_wait(&hout->empty[slot], (sent / HRS - 1) & 1u);
+      hout->ring[slot][i] = dx;
+      ++sent;
+      __syncwarp();
+      if (i == 0) mbar_arrive(&hout->full[slot]);
+    }
+    __syncwarp();                                        // sh_c / sh_r / sh_u free for the next step
+  };
+
+  for (int it = 0; it < nch; ++it) {
+    const int ci = nch - 1 - it;
+    const int stage = it % NS;
+    const int s0 = ci * CH;
+    const int len = min(CH, S - s0);
+    mbar_wait(&full[stage], (uint32_t)(it / NS) & 1u);
+    float* ob = s_da + (it & 1) * CH * G3;
+    if (it >= 2) {
+      if (i == 0) bulk_wait_read<1>();
+      __syncwarp();
+    }
+    const float* ib = s_st + stage * (CH + 1) * ST;
+    if (len == CH && s0 > 0) {
+#pragma unroll 2                                         // deeper unrolling spills at the 168-register cap
+      for (int t = CH - 1; t >= 0; --t) step(ib + t * ST, ob + t * G3, false);
+    } else {
+      for (int t = len - 1; t >= 0; --t) step(ib + t * ST, ob + t * G3, s0 + t == 0);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (i == 0) {
+      bulk_s2g(dab + (int64_t)s0 * G3, ob, (uint32_t)len * G3 * 4);
+      bulk_commit();
+      if (it + NS < nch) issue(nch - 1 - (it + NS), stage);
+    }
+  }
+  if (i == 0) bulk_wait_read<0>();
+  __syncwarp();
+}
+
+// Registers are partitioned per SM sub-partition (16 K each): 10 warps = 3 on one SMSP = at most 168 per thread.
+__global__ void __launch_bounds__(320)
+wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int tid = threadIdx.x, w = tid >> 5, i = tid & 31;
+  const int L = a.L, nspc = a.nspc;
+  const int k = L - 1 - w / nspc, si = w % nspc;        // layer 0 (the critical path) = highest warp ids
+  const int b = blockIdx.x * nspc + si;
+  const WaveBwdSmem sm(L, nspc);
+  float2* sWxT = reinterpret_cast<float2*>(dsm + sm.wxt);
+  Handoff* hand = reinterpret_cast<Handoff*>(dsm + sm.hand);
+
+  // ---- CTA setup: W_x^T of layers >= 1 as pairs over n: sWxT[kk-1][q][i] = (WxT[2q][i], WxT[2q+1][i]) ----
+  for (int e = tid; e < (L - 1) * 48 * HP; e += blockDim.x) {
+    const int kk = 1 + e / (48 * HP), r = e % (48 * HP);
+    const int q = r / HP, ii = r % HP;
+    const float* WxT = a.pw + a.WxT[kk];                 // [96][32]
+    sWxT[e] = make_float2(__ldg(WxT + (2 * q) * HP + ii), __ldg(WxT + (2 * q + 1) * HP + ii));
+  }
+  for (int e = tid; e < (L - 1) * nspc * HRS; e += blockDim.x) {
+    mbar_init(&hand[e / HRS].full[e % HRS], 1);
+    mbar_init(&hand[e / HRS].empty[e % HRS], 1);
+  }
+  fence_mbar_init();
+  __syncthreads();
+  if (b >= a.B) return;
+
+  Handoff* hin = k < L - 1 ? &hand[k * nspc + si] : nullptr;        // from layer k+1
+  Handoff* hout = k > 0 ? &hand[(k - 1) * nspc + si] : nullptr;     // to layer k-1
+  if (k == 0) {
+    wave_bwd_layer<BCH0, BNS0>(a, k, b, i, dsm + sm.l0 + si * bwd_region_bytes(BCH0, BNS0), hin, nullptr, nullptr);
+  } else {
+    wave_bwd_layer<BCHK, BNSK>(a, k, b, i, dsm + sm.lk + ((k - 1) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
+                               sWxT + (size_t)(k - 1) * 48 * HP);
+  }
+}
+
+bool launch_wave_bwd(const Launch& L, const Dims& d, const PackLayout& pk, const float* pw, const float* const* st,
+                     float* const* da, const float* dmemory, cudaStream_t st_) {
+  if (d.L > WAVE_MAX_L) return false;
+  const int nspc = d.L <= 5 ? 2 : 1;
+  const WaveBwdSmem sm(d.L, nspc);
+  if (sm.total > 220 * 1024) return false;
+  WaveBwdArgs a; memset(&a, 0, sizeof(a));
+  a.pw = pw; a.dmemory = dmemory;
+  a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
+  for (int k = 0; k < d.L; ++k) { a.st[k] = st[k]; a.da[k] = da[k]; a.WhT[k] = pk.WhT[k]; a.WxT[k] = pk.WxT[k]; a.S[k] = d.S[k]; a.P[k] = d.P[k]; }
+  cudaFuncSetAttribute(wave_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+  const int grid = (d.B + nspc - 1) / nspc;
+  wave_bwd_kernel<<<grid, 32 * d.L * nspc, sm.total, st_>>>(a);
+  { cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_bwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * d.L * nspc, sm.total); return false; } }
   ++*L.counter;
   return true;
 }
