@@ -253,7 +253,6 @@ tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restr
 
   if (warp < WPW) {
     // ================= producers =================
-    // two register buffers: the global loads of stage s+2 are in flight while stage s+1 is converted and stored
     struct Regs { float4 x[NX], h[1], r[1], d[3]; };
     Regs bufA, bufB;
     // work unit u = warp + 4*i covers 16 rows x 2 adjacent 16-byte chunks: every 32-byte sector a warp touches is
@@ -312,15 +311,18 @@ tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restr
       fence_proxy_async();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
     };
+    // four register buffers: ~80 KB of global loads in flight per SM (6.5 TB/s x ~1.5 us needs ~66 KB per SM)
+    Regs bufC, bufD;
     load(bufA, 0);
     load(bufB, 1);
-    for (int sidx = 0; sidx < nst; sidx += 2) {
+    load(bufC, 2);
+    load(bufD, 3);
+    for (int sidx = 0; sidx < nst; sidx += 4) {
       store(bufA, sidx);
-      load(bufA, sidx + 2);
-      if (sidx + 1 < nst) {
-        store(bufB, sidx + 1);
-        load(bufB, sidx + 3);
-      }
+      load(bufA, sidx + 4);
+      if (sidx + 1 < nst) { store(bufB, sidx + 1); load(bufB, sidx + 5); }
+      if (sidx + 2 < nst) { store(bufC, sidx + 2); load(bufC, sidx + 6); }
+      if (sidx + 3 < nst) { store(bufD, sidx + 3); load(bufD, sidx + 7); }
     }
     // ================= epilogue (warps 0-3): TMEM lane = input feature =================
     if (warp < 4) {

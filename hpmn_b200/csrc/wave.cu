@@ -115,28 +115,37 @@ __device__ __forceinline__ float wave_layer(const WaveArgs& a, int k, int b, int
   unsigned fired = 0, s_glob = 0;                        // hand-offs produced / consumed so far
   int to_fire = period;
 
+  // layers >= 1: input projection of hand-off `idx` (hidden state of layer k-1 at its step (idx+1)*p_{k-1} - 1,
+  // hpmn.py:124-128).  It does not depend on this layer's state, so it is issued one step ahead and overlaps the
+  // latency bubbles of the recurrent chain.
+  auto project = [&](unsigned idx, float& ar, float& au, float& ac) {
+    const int slot_in = idx & (HRS - 1);
+    mbar_wait(&hin->full[slot_in], (idx / HRS) & 1u);                // hardware-suspended wait, no polling
+    const float4* x4 = reinterpret_cast<const float4*>(hin->ring[slot_in]);
+    float2 p0 = make_float2(myBx[j], 0.f), p1 = make_float2(myBx[HP + j], 0.f), p2 = make_float2(myBx[2 * HP + j], 0.f);
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      const float4 x = x4[q4];
+      const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+      const float2* wq = myWx + (2 * q4) * 3 * HP + j;
+      p0 = ffma2(xa, wq[0], p0); p1 = ffma2(xa, wq[HP], p1); p2 = ffma2(xa, wq[2 * HP], p2);
+      p0 = ffma2(xb, wq[3 * HP], p0); p1 = ffma2(xb, wq[4 * HP], p1); p2 = ffma2(xb, wq[5 * HP], p2);
+    }
+    ar = p0.x + p0.y; au = p1.x + p1.y; ac = p2.x + p2.y;
+    __syncwarp();
+    if (j == 0) mbar_arrive(&hin->empty[slot_in]);       // slot free again
+  };
+  float nar = 0.f, nau = 0.f, nac = 0.f;                 // projections of the NEXT step (layers >= 1)
+  if (!IS_L0) project(0, nar, nau, nac);
+
   auto step = [&](const float* ib, float* orow) {
     float ar, au, ac;
     if (IS_L0) {
       ar = ib[j]; au = ib[HP + j]; ac = ib[2 * HP + j];
     } else {
-      // input = hidden state of layer k-1 at its step (s+1)*p_{k-1} - 1 (hpmn.py:124-128), through the hand-off ring
-      const int slot_in = s_glob & (HRS - 1);
-      mbar_wait(&hin->full[slot_in], (s_glob / HRS) & 1u);           // hardware-suspended wait, no polling
-      const float4* x4 = reinterpret_cast<const float4*>(hin->ring[slot_in]);
-      float2 p0 = make_float2(myBx[j], 0.f), p1 = make_float2(myBx[HP + j], 0.f), p2 = make_float2(myBx[2 * HP + j], 0.f);
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 x = x4[q4];
-        const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
-        const float2* wq = myWx + (2 * q4) * 3 * HP + j;
-        p0 = ffma2(xa, wq[0], p0); p1 = ffma2(xa, wq[HP], p1); p2 = ffma2(xa, wq[2 * HP], p2);
-        p0 = ffma2(xb, wq[3 * HP], p0); p1 = ffma2(xb, wq[4 * HP], p1); p2 = ffma2(xb, wq[5 * HP], p2);
-      }
-      ar = p0.x + p0.y; au = p1.x + p1.y; ac = p2.x + p2.y;
-      __syncwarp();
-      if (j == 0) mbar_arrive(&hin->empty[slot_in]);     // slot free again
+      ar = nar; au = nau; ac = nac;
       ++s_glob;
+      if (s_glob < (unsigned)S) project(s_glob, nar, nau, nac);
     }
     const float r = sigmoid_f(dotn(hprev, wr, ar));      // util.py:95-96
     const float u = sigmoid_f(dotn(hprev, wu, au));
@@ -172,8 +181,13 @@ __device__ __forceinline__ float wave_layer(const WaveArgs& a, int k, int b, int
       __syncwarp();
     }
     if (len == CH) {
+      if constexpr (IS_L0) {
 #pragma unroll 4
-      for (int t = 0; t < CH; ++t) step(ib + t * G3, ob + t * ST);
+        for (int t = 0; t < CH; ++t) step(ib + t * G3, ob + t * ST);
+      } else {
+#pragma unroll 2                                         // deeper unrolling spills at the 168-register cap
+        for (int t = 0; t < CH; ++t) step(ib + t * G3, ob + t * ST);
+      }
     } else {
       for (int t = 0; t < len; ++t) step(ib + t * G3, ob + t * ST);
     }
