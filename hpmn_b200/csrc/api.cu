@@ -223,15 +223,17 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
       cudaStream_t ws = st;
       if (ov) { cudaEventRecord(ctx->ev_fork[0], st); cudaStreamWaitEvent(ctx->side, ctx->ev_fork[0], 0); ws = ctx->side; }
       { Bracket b(ctx, st, HPMN_K_WGRAD);
+        const float* xa[HPMN_MAX_LAYERS]; int64_t lx[HPMN_MAX_LAYERS];
+        float *gWg[HPMN_MAX_LAYERS], *gbg[HPMN_MAX_LAYERS], *gWc[HPMN_MAX_LAYERS], *gbc[HPMN_MAX_LAYERS];
         for (int k = 0; k < d.L; ++k) {
-          const float* A = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;
-          const int64_t lda = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
-          float* da = dap[k];
-          if (!(ctx->use_tc && launch_tc_wgrad(L, d, k, A, lda, p.f(p.wl.st[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
-                                               grads + p.pl.Wc[k], grads + p.pl.bc[k], ws)))
-            launch_gru_wgrad(L, d, k, A, lda, p.f(p.wl.st[k]), da, grads + p.pl.Wg[k], grads + p.pl.bg[k],
-                             grads + p.pl.Wc[k], grads + p.pl.bc[k], ws);
-        } }
+          xa[k] = k == 0 ? x : p.f(p.wl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;
+          lx[k] = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
+          gWg[k] = grads + p.pl.Wg[k]; gbg[k] = grads + p.pl.bg[k]; gWc[k] = grads + p.pl.Wc[k]; gbc[k] = grads + p.pl.bc[k];
+        }
+        if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, ws)))
+          for (int k = 0; k < d.L; ++k)
+            launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], ws);
+      }
       { Bracket b(ctx, st, HPMN_K_DX);
         dense_gemm(ctx, L, dap[0], G3, pw + p.pk.WxT[0], nullptr, dx0, (int64_t)d.B * d.S[0], d.DinP[0], G3, st); }
       if (ov) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }

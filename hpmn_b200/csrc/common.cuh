@@ -301,6 +301,10 @@ bool launch_tc_gemm_nn(const Launch&, const float* A, int64_t lda, const float* 
 // GRU weight gradients on tcgen05 (same contract as launch_gru_wgrad); false when the shape has no instantiation
 bool launch_tc_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_t ldx, const float* st, const float* da,
                      float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_);
+// every layer in one launch per padded input width (per-layer arrays of length d.L); false if a layer has no instantiation
+bool launch_tc_wgrad_all(const Launch&, const Dims&, const float* const* xin, const int64_t* ldx, const float* const* st,
+                         const float* const* da, float* const* dWg, float* const* dbg, float* const* dWc, float* const* dbc,
+                         cudaStream_t st_);
 // batched C[I,N](ldc) += sum_m A[m,I](lda) * Bm[m,N](ldb) with atomic accumulation; A == nullptr -> ones
 struct AtbProb {
   const float* A; const float* Bm; float* C;

@@ -210,12 +210,27 @@ __device__ __forceinline__ void put_t(unsigned char* hi_base, unsigned char* lo_
 
 constexpr int WPW = 8;                 // producer warps (2 per SM sub-partition: the convert/transposing stores are issue-bound)
 
+// one launch serves every layer that shares the padded input width: CTA -> (layer, row range)
+struct WgradProb {
+  const float* xin; const float* st; const float* da;
+  float* dWg; float* dbg; float* dWc; float* dbc;
+  int64_t ldx, M, rows_per_cta;
+  int S, Din, cta_begin, pad_;
+};
+struct WgradBatch { int n, H; WgradProb p[HPMN_MAX_LAYERS]; };
+
 template <int DINP>
 __global__ void __launch_bounds__(32 * (WPW + 1))
-tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restrict__ st, const float* __restrict__ da,
-                float* __restrict__ dWg, float* __restrict__ dbg, float* __restrict__ dWc, float* __restrict__ dbc, int64_t M,
-                int S, int Din, int H, int64_t rows_per_cta) {
+tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   static_assert(DINP + 64 < 128, "the ones row needs a free feature slot");
+  int pi = 0;
+  while (pi + 1 < batch.n && (int)blockIdx.x >= batch.p[pi + 1].cta_begin) ++pi;
+  const WgradProb& P = batch.p[pi];
+  const float* __restrict__ xin = P.xin; const float* __restrict__ st = P.st; const float* __restrict__ da = P.da;
+  float* __restrict__ dWg = P.dWg; float* __restrict__ dbg = P.dbg; float* __restrict__ dWc = P.dWc; float* __restrict__ dbc = P.dbc;
+  const int64_t ldx = P.ldx, M = P.M, rows_per_cta = P.rows_per_cta;
+  const int S = P.S, Din = P.Din, H = batch.H;
+  const int cta = (int)blockIdx.x - P.cta_begin;
   constexpr int XC = DINP / 4;           // feature chunks of x
   constexpr int NXU = XC;                // work units (16 rows x 2 chunks) in the x part
   constexpr int NX = (NXU + WPW - 1) / WPW;
@@ -226,7 +241,7 @@ tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restr
   uint64_t* done = empty + WNS;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t mbeg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t mbeg = (int64_t)cta * rows_per_cta;
   const int64_t mend = mbeg + rows_per_cta < M ? mbeg + rows_per_cta : M;
   const int nst = mend > mbeg ? (int)((mend - mbeg + WK - 1) / WK) : 0;
 
@@ -382,20 +397,60 @@ tc_wgrad_kernel(const float* __restrict__ xin, int64_t ldx, const float* __restr
   if (warp == WPW) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
+static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin, int64_t ldx, const float* st, const float* da,
+                            float* dWg, float* dbg, float* dWc, float* dbc, int64_t M, int S, int Din, int64_t total_rows) {
+  WgradProb& P = b.p[b.n++];
+  P.xin = xin; P.st = st; P.da = da; P.dWg = dWg; P.dbg = dbg; P.dWc = dWc; P.dbc = dbc; P.ldx = ldx; P.M = M; P.S = S; P.Din = Din;
+  const int64_t stages = (M + WK - 1) / WK;
+  int64_t want = (int64_t)((double)sms * (double)M / (double)total_rows + 0.5);   // CTAs proportional to the layer's rows
+  if (want > stages / 4) want = stages / 4;                                        // >= 4 stages per CTA
+  if (want < 1) want = 1;
+  P.rows_per_cta = ((stages + want - 1) / want) * WK;
+  const int n = (int)((M + P.rows_per_cta - 1) / P.rows_per_cta);
+  P.cta_begin = ctas;
+  ctas += n;
+}
+
+bool launch_tc_wgrad_all(const Launch& L, const Dims& d, const float* const* xin, const int64_t* ldx, const float* const* st,
+                         const float* const* da, float* const* dWg, float* const* dbg, float* const* dWc, float* const* dbc,
+                         cudaStream_t st_) {
+  for (int k = 0; k < d.L; ++k)
+    if (d.DinP[k] != 32 && d.DinP[k] != 48) return false;
+  WgradBatch b32, b48; b32.n = b48.n = 0; b32.H = b48.H = d.H;
+  int c32 = 0, c48 = 0;
+  int64_t rows32 = 0, rows48 = 0;
+  for (int k = 0; k < d.L; ++k) (d.DinP[k] == 32 ? rows32 : rows48) += (int64_t)d.B * d.S[k];
+  for (int k = 0; k < d.L; ++k) {
+    const int64_t M = (int64_t)d.B * d.S[k];
+    if (d.DinP[k] == 32) wgrad_queue_add(b32, c32, L.sms, xin[k], ldx[k], st[k], da[k], dWg[k], dbg[k], dWc[k], dbc[k], M, d.S[k], d.Din[k], rows32);
+    else wgrad_queue_add(b48, c48, L.sms, xin[k], ldx[k], st[k], da[k], dWg[k], dbg[k], dWc[k], dbc[k], M, d.S[k], d.Din[k], rows48);
+  }
+  const size_t smem = (size_t)WNS * W_STAGE + 128;
+  if (b48.n) {
+    cudaFuncSetAttribute(tc_wgrad_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_wgrad_kernel<48><<<c48, 32 * (WPW + 1), smem, st_>>>(b48);
+    ++*L.counter;
+  }
+  if (b32.n) {
+    cudaFuncSetAttribute(tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_wgrad_kernel<32><<<c32, 32 * (WPW + 1), smem, st_>>>(b32);
+    ++*L.counter;
+  }
+  return true;
+}
+
 bool launch_tc_wgrad(const Launch& L, const Dims& d, int k, const float* xin, int64_t ldx, const float* st, const float* da,
                      float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_) {
   const int DinP = d.DinP[k];
   if (DinP != 32 && DinP != 48) return false;
+  WgradBatch b; b.n = 0; b.H = d.H;
+  int ctas = 0;
   const int64_t M = (int64_t)d.B * d.S[k];
+  wgrad_queue_add(b, ctas, L.sms, xin, ldx, st, da, dWg, dbg, dWc, dbc, M, d.S[k], d.Din[k], M);
   const size_t smem = (size_t)WNS * W_STAGE + 128;
-  int64_t stages = (M + WK - 1) / WK;
-  int64_t ctas = stages / 8 < L.sms ? stages / 8 : L.sms;      // >= 8 stages per CTA: every CTA ends with ~12 k atomics
-  if (ctas < 1) ctas = 1;
-  const int64_t rpc = ((stages + ctas - 1) / ctas) * WK;
-  ctas = (M + rpc - 1) / rpc;
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)ctas, 32 * (WPW + 1), smem, st_>>>(xin, ldx, st, da, dWg, dbg, dWc, dbc, M, d.S[k], d.Din[k], d.H, rpc);
+    kern<<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
   };
   if (DinP == 32) go(tc_wgrad_kernel<32>); else go(tc_wgrad_kernel<48>);
   ++*L.counter;
