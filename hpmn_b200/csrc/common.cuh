@@ -247,9 +247,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   int spins = 0;
   do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (!done && ++spins > (1 << 22)) __trap();      // a lost transaction must abort, never hang the GPU
+    // the suspend-time hint keeps a blocked warp parked in hardware (no spurious wake-ups stealing issue slots)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    if (!done && ++spins > (1 << 16)) __trap();      // a lost transaction must abort, never hang the GPU
   } while (!done);
 }
 // global -> shared, completion counted in bytes on `bar`
