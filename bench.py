@@ -220,6 +220,8 @@ def run_product(args, cfg_name, cfg):
     steps_all = sh.steps()
     fl_rec_fwd = B * sum(s * 2 * sh.H * 3 * sh.H for s in steps_all)                 # recurrent half, per launch set
     fl_gru_fwd = B * sh.gru_flops_fwd_per_sample()
+    fl_upper_x = B * sum(s * 2 * sh.H * 3 * sh.H for s in steps_all[1:])             # x-half of layers >= 1 (in the wavefront kernels)
+    fl_l0_x = fl_gru_fwd - fl_rec_fwd - fl_upper_x                                   # x-half of layer 0 (tcgen05 GEMM)
     fams = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
     gather_bytes = sh.gather_bytes() + B * sh.Tpad * sh.D * 4
     scatter_bytes = sh.gather_bytes() + 2 * 4 * sh.E * B * sh.T * sh.F
@@ -231,15 +233,26 @@ def run_product(args, cfg_name, cfg):
         fams["scatter_add"]["frac_of_hbm_peak"] = fams["scatter_add"]["GBps"] / hbm_peak
     dom = max(fams, key=lambda k: fams[k]["ms_per_step"])
     dom_ms = fams[dom]["ms_per_step"]
-    flops_by_family = {"rec_fwd": fl_rec_fwd, "rec_bwd": fl_rec_fwd, "inproj_gemm": fl_gru_fwd - fl_rec_fwd,
-                       "dx_gemm": fl_gru_fwd - fl_rec_fwd, "gru_wgrad": fl_gru_fwd}
+    wave = fams.get("rec_fwd", {}).get("launches_per_step", 0) == 1 and sh.L > 1   # fused wavefront kernels in use
+    flops_by_family = {"rec_fwd": fl_rec_fwd + (fl_upper_x if wave else 0), "rec_bwd": fl_rec_fwd + (fl_upper_x if wave else 0),
+                       "inproj_gemm": fl_l0_x if wave else fl_gru_fwd - fl_rec_fwd,
+                       "dx_gemm": fl_l0_x if wave else fl_gru_fwd - fl_rec_fwd, "gru_wgrad": fl_gru_fwd}
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
     if dom in flops_by_family:
         achieved = flops_by_family[dom] / (dom_ms * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12       # FFMA lanes x 2 flop x max SM clock
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_flops_per_step": flops_by_family[dom], "kernel_ms_per_step": dom_ms,
-                "note": "fp32 FFMA2 kernel (1e-4 parity rules out single-pass tf32/bf16 tensor-core math through 1024 "
-                        "recurrent steps); latency-bound at B=256 -- see DESIGN.md. fp32 CUDA-core peak ~74 TFLOP/s."}
+                "frac": achieved / tf_peak, "traffic": ncu_traffic.get(dom) if cfg_name == "xlong" and B == 256 else None,
+                "peak_source": peak_src, "algorithmic_flops_per_step": flops_by_family[dom], "kernel_ms_per_step": dom_ms,
+                "frac_of_fp32_ffma_peak": achieved / fp32_peak,
+                "note": "dense contraction, so reported against the measured tensor peak; the kernel itself is an fp32 FFMA2 "
+                        "recurrence (1e-4 parity through 1024 dependent steps rules out single-pass tf32/bf16; M>=64 tcgen05 tiles "
+                        "would occupy 2-4 SMs at B=256) and is latency-bound by construction -- DESIGN.md section 4. "
+                        "The dense halves run on tcgen05 (inproj_gemm, dx_gemm, gru_wgrad in `kernels`).",
+                "traffic_source": ncu_traffic.get("source")}
     else:
         byts = gather_bytes if dom == "gather_fwd" else scatter_bytes
         achieved = byts / (dom_ms * 1e-3) / 1e9

@@ -53,6 +53,10 @@ CASES = {
     "single_layer_E8_H16": (HpmnShape(B=3, T=7, F=2, E=8, H=16, periods=[], L=1, hops=1, V=50), True),
     "one_sample_ragged_T": (HpmnShape(B=1, T=18, F=2, E=16, H=32, periods=[3, 2], L=3, hops=3, V=64), True),
     "many_rows_B67": (HpmnShape(B=67, T=16, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=97), True),
+    # 6 layers: the wavefront kernels switch to one sample per CTA; mixed periods 2,3,1,2,5
+    "deep_L6_mixed_periods": (HpmnShape(B=5, T=120, F=2, E=16, H=32, periods=[2, 3, 1, 2, 5], L=6, hops=2, V=211), True),
+    # long enough for several TMA chunks per layer and a ragged last chunk (T=75 -> 75/25/5 steps)
+    "ragged_chunks_T75": (HpmnShape(B=4, T=75, F=2, E=16, H=24, periods=[3, 5], L=3, hops=3, V=131), True),
 }
 
 
@@ -81,6 +85,33 @@ def test_forward_backward_matches_oracle(name, mode):
     got = eng.named_grads(); got["Embedding/emb_mtx"] = eng.dtable.cpu().numpy()
     _grad_close(got, g_ref)
     assert eng.launch_count() > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("env", [{"HPMN_NO_WAVE": "1"}, {"HPMN_NO_TC": "1"}, {"HPMN_NO_WAVE": "1", "HPMN_NO_TC": "1"},
+                                 {"HPMN_GROUPS": "3", "HPMN_GROUP_MIN_ROWS": "16"}, {"HPMN_NO_OVERLAP": "1"}],
+                         ids=["layer_serial", "ffma_gemms", "layer_serial_ffma", "row_groups", "no_side_stream"])
+def test_alternate_kernel_paths_match_oracle(env, monkeypatch):
+    """The library picks its kernels at hpmn_create() from the environment: the per-layer recurrent kernels, the fp32
+    FFMA GEMMs, the concurrent row-group streams and the single-stream schedule must all give the same answer."""
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sh = HpmnShape(B=48, T=40, F=2, E=16, H=32, periods=[2, 2, 5], L=4, hops=3, V=300, front_pad=0)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, seed=4321, mode="stress", dtype=np.float32)
+    ids, labels = O.synthetic_batch(osh, seed=1234, ragged=True)
+    fwd = O.forward(osh, params, table, ids, labels, memory_reg=1e-3, dtype=np.float64)
+    g_ref, dt_ref = O.backward(osh, fwd, ids, labels, memory_reg=1e-3)
+    eng = _engine(sh, params, table, 1e-3)
+    eng.forward_backward(torch.as_tensor(ids, device=eng.device), torch.as_tensor(labels, device=eng.device))
+    torch.cuda.synchronize()
+    _close(eng.memory.cpu().numpy(), fwd["memory"], "memory")
+    _close(eng.logit.cpu().numpy(), fwd["logit"], "logit")
+    _close(eng.scalars.cpu().numpy()[:3], [fwd["logloss"], fwd["covreg"], fwd["loss"]], "scalars")
+    g_ref = dict(g_ref); g_ref["Embedding/emb_mtx"] = dt_ref
+    got = eng.named_grads(); got["Embedding/emb_mtx"] = eng.dtable.cpu().numpy()
+    _grad_close(got, g_ref)
     eng.close()
 
 
