@@ -107,14 +107,24 @@ class Hpmn_Basic(object):
 
     def train_on_batch(self, data):
         ids, labels = self._feed(data)
+        if len(labels) > self.max_batch:
+            raise ValueError("train batch %d exceeds max_batch=%d (pass a larger max_batch)" % (len(labels), self.max_batch))
         self._step_seed += 1
         self.engine.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=self._step_seed)   # hpmn.py:480
         self.engine.apply_gradients(self.learning_rate)                                                # hpmn.py:209-214
 
     def predict_on_batch(self, data):
+        """eval fetch; batches larger than the engine capacity are evaluated in chunks (rows are independent; the
+        memory loss is a sum over rows, hpmn.py:170)."""
         ids, labels = self._feed(data)
-        scalars, pred = self.engine.step_host(ids, labels, with_backward=False, keep_prob=1.0)         # hpmn.py:509
-        return float(scalars[1]), pred.copy(), self.engine.h_w_hop0.numpy()[: len(labels)].copy()
+        mem, preds, weights = 0.0, [], []
+        for lo in range(0, len(labels), self.max_batch):
+            hi = min(len(labels), lo + self.max_batch)
+            scalars, pred = self.engine.step_host(ids[lo:hi], labels[lo:hi], with_backward=False, keep_prob=1.0)   # hpmn.py:509
+            mem += float(scalars[1])
+            preds.append(pred.copy())
+            weights.append(self.engine.h_w_hop0.numpy().reshape(-1)[: (hi - lo) * self.shape.L].reshape(hi - lo, self.shape.L).copy())
+        return mem, np.concatenate(preds), np.concatenate(weights)
 
     # ---- hpmn.py:467-495 / 322-349
     def train(self, epochs, batchsize):
