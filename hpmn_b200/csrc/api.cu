@@ -14,6 +14,7 @@ using namespace hpmn;
 #define HPMN_MAX_GROUPS 4
 
 struct hpmn_ctx {
+  bool wave_now;    // decided per step: the wavefront kernels are used only when the whole batch is one wave of CTAs
   bool use_wave;    // fused wavefront kernels for the recurrence (HPMN_NO_WAVE=1 selects the layer-by-layer kernels)
   bool use_tc;      // tcgen05 path for the dense (non-recurrent) GEMMs; HPMN_NO_TC=1 selects the FFMA kernels
   int device;
@@ -25,8 +26,8 @@ struct hpmn_ctx {
   // caller's stream (forked / joined with events, so the caller still sees plain stream order)
   cudaStream_t side;
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
-  cudaEvent_t ev_join;
-  bool overlap;
+  cudaEvent_t ev_join, ev_zero;
+  bool overlap, zero_pending;
   // row groups: the batch is cut into `groups` independent row ranges, each running its whole fwd+bwd chain on its own
   // stream, so one group's dense kernels fill the SMs while another group sits in its latency-bound recurrence
   int groups, group_min_rows;
@@ -185,7 +186,7 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
   { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
-  if (ctx->use_wave && d.L <= 10) {
+  if (ctx->use_wave && ctx->wave_now && d.L <= 10) {
     // layer-0 input projections (dense, tensor cores), then every layer of every sample as one wavefront kernel
     { Bracket b(ctx, st, HPMN_K_INPROJ);
       dense_gemm(ctx, L, x, d.D, pw + p.pk.Wx[0], pw + p.pk.bx[0], p.f(p.wl.proj[0]), (int64_t)d.B * d.S[0], G3, d.DinP[0], st); }
@@ -211,7 +212,7 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
-  if (ctx->use_wave && d.L <= 10) {
+  if (ctx->use_wave && ctx->wave_now && d.L <= 10) {
     // every layer's reverse-time recurrence as one wavefront kernel (dx of layers >= 1 handed down in-kernel); then the
     // dense work: layer-0 dX (feeds the embedding scatter) on `st`, all weight-gradient reductions on the side stream
     const float* stp[HPMN_MAX_LAYERS]; float* dap[HPMN_MAX_LAYERS];
@@ -292,7 +293,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx = new (std::nothrow) hpmn_ctx();
   if (!ctx) return fail(nullptr, HPMN_ENOMEM, "out of host memory");
   ctx->device = device; ctx->sms = prop.multiProcessorCount; ctx->launches = 0; ctx->err[0] = 0;
-  ctx->profile = false; ctx->pool_used = 0;
+  ctx->profile = false; ctx->pool_used = 0; ctx->wave_now = true;
   { const char* e_tc = getenv("HPMN_NO_TC"); ctx->use_tc = !(e_tc && e_tc[0] == '1'); }
   { const char* e_w = getenv("HPMN_NO_WAVE"); ctx->use_wave = !(e_w && e_w[0] == '1'); }
   memset(ctx->ms, 0, sizeof(ctx->ms)); memset(ctx->calls, 0, sizeof(ctx->calls));
@@ -302,6 +303,8 @@ int hpmn_create(hpmn_ctx** out, int device) {
   cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
   for (auto& ev : ctx->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_zero, cudaEventDisableTiming);
+  ctx->zero_pending = false;
   { const char* e_ov = getenv("HPMN_NO_OVERLAP"); ctx->overlap = !(e_ov && e_ov[0] == '1'); }
   for (auto& gs : ctx->gstream) cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking);
   for (auto& ev : ctx->ev_gdone) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -317,6 +320,7 @@ void hpmn_destroy(hpmn_ctx* ctx) {
   for (auto e : ctx->pool) cudaEventDestroy(e);
   for (auto& ev : ctx->ev_fork) cudaEventDestroy(ev);
   cudaEventDestroy(ctx->ev_join);
+  cudaEventDestroy(ctx->ev_zero);
   cudaStreamDestroy(ctx->side);
   for (auto& gs : ctx->gstream) cudaStreamDestroy(gs);
   for (auto& ev : ctx->ev_gdone) cudaEventDestroy(ev);
@@ -408,6 +412,7 @@ int hpmn_memory_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const fl
   Plan p; int rc = make_plan(ctx, s, workspace, p);
   if (rc) return rc;
   if (!x || !params || !memory) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  { const int nspc = p.d.L <= 5 ? 2 : 1; ctx->wave_now = (p.d.B + nspc - 1) / nspc <= ctx->sms; }
   run_memory_fwd(ctx, p, x, params, memory, (cudaStream_t)stream);
   return check_launch(ctx, "hpmn_memory_fwd");
 }
@@ -420,6 +425,7 @@ int hpmn_memory_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const fl
   cudaStream_t st = (cudaStream_t)stream;
   Launch L{&ctx->launches, ctx->sms};
   launch_pack(L, p.d, p.pl, p.pk, params, p.f(p.wl.pw), st);
+  { const int nspc = p.d.L <= 5 ? 2 : 1; ctx->wave_now = (p.d.B + nspc - 1) / nspc <= ctx->sms; }
   run_memory_bwd(ctx, p, x, dmemory, dx, grads, ctx->overlap && !ctx->profile, st);
   return check_launch(ctx, "hpmn_memory_bwd");
 }
@@ -521,6 +527,7 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
       launch_atb_batch(L, batch, st);
     } }
   run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), p.f(p.wl.dxk[0]), grads, ov, st);
+  if (ctx->zero_pending) { cudaStreamWaitEvent(st, ctx->ev_zero, 0); ctx->zero_pending = false; }
   { Bracket b(ctx, st, HPMN_K_SCATTER);
     launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids + (int64_t)r0 * d.T * d.F,
                       p.f(p.wl.dxk[0]), p.f(p.wl.dlast), dtable, st); }
@@ -533,15 +540,32 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   if (hy.loss_batch <= 0) hy.loss_batch = d.B;          // the groups must divide the log-loss by the whole batch
+  // Wavefront kernels: 2 samples per CTA (1 for L > 5), one CTA per SM (shared memory).  They minimise the latency of
+  // one wave; with more samples than one wave holds, the per-layer kernels (one warp per sample, ~12 resident per SM)
+  // have the higher throughput (tools/microbench.py).
+  { const int nspc = d.L <= 5 ? 2 : 1; ctx->wave_now = (d.B + nspc - 1) / nspc <= ctx->sms; }
   // co-running dense kernels steal issue slots from the latency-critical recurrent warps, so grouping only pays
   // once every group still fills the machine (measured: -4 % at B=256, +11 % at B=1024)
   int G = ctx->profile ? 1 : ctx->groups;
   while (G > 1 && d.B / G < ctx->group_min_rows) --G;
+  ctx->zero_pending = false;
   { Bracket b(ctx, st, HPMN_K_MISC);
     CK(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
     if (with_backward) {
       CK(cudaMemsetAsync(grads, 0, (size_t)p.pl.total * sizeof(float), st));
-      if (zero_dtable) CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st));
+      if (zero_dtable) {
+        if (G == 1 && ctx->overlap && !ctx->profile) {
+          // the table gradient is only touched by the scatter at the very end: zero its 212 MB on the side stream, behind
+          // the forward pass, and make the scatter wait for it
+          CK(cudaEventRecord(ctx->ev_fork[HPMN_MAX_LAYERS + 1], st));
+          CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS + 1], 0));
+          CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), ctx->side));
+          CK(cudaEventRecord(ctx->ev_zero, ctx->side));
+          ctx->zero_pending = true;
+        } else {
+          CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st));
+        }
+      }
     } }
   if (G == 1) {
     fwd_rows(ctx, p, s, hy, ids, labels, params, table, scalars, st);

@@ -310,18 +310,22 @@ __device__ __forceinline__ float wave_layer(const WaveArgs& a, int k, int b, int
 // Helper warp of layer 1 (forward): applies W_x^(1) to every hand-off of layer 0 so that layer 1's recurrent warp has the
 // same per-step cost as layer 0's while running at half its rate.
 __device__ __forceinline__ void wave_proj_helper(int n, int j, const float2* myWx, const float* myBx, Handoff* hin, Handoff3* hout3) {
+  // W_x of layer 1 in registers (this warp has no other state): no shared-memory traffic competing with layer 0's broadcasts
+  float2 w0[16], w1[16], w2[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { w0[q] = myWx[(q * 3 + 0) * HP + j]; w1[q] = myWx[(q * 3 + 1) * HP + j]; w2[q] = myWx[(q * 3 + 2) * HP + j]; }
+  const float b0 = myBx[j], b1 = myBx[HP + j], b2 = myBx[2 * HP + j];
   for (unsigned idx = 0; idx < (unsigned)n; ++idx) {
     const int slot = idx & (HRS - 1), g = (idx / HG) & 1;
     if ((idx & (HG - 1)) == 0) mbar_wait(&hin->gfull[g], (idx / HRS) & 1u);
     const float4* x4 = reinterpret_cast<const float4*>(hin->ring[slot]);
-    float2 p0 = make_float2(myBx[j], 0.f), p1 = make_float2(myBx[HP + j], 0.f), p2 = make_float2(myBx[2 * HP + j], 0.f);
+    float2 p0 = make_float2(b0, 0.f), p1 = make_float2(b1, 0.f), p2 = make_float2(b2, 0.f);
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
       const float4 x = x4[q4];
       const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
-      const float2* wq = myWx + (2 * q4) * 3 * HP + j;
-      p0 = ffma2(xa, wq[0], p0); p1 = ffma2(xa, wq[HP], p1); p2 = ffma2(xa, wq[2 * HP], p2);
-      p0 = ffma2(xb, wq[3 * HP], p0); p1 = ffma2(xb, wq[4 * HP], p1); p2 = ffma2(xb, wq[5 * HP], p2);
+      p0 = ffma2(xa, w0[2 * q4], p0); p1 = ffma2(xa, w1[2 * q4], p1); p2 = ffma2(xa, w2[2 * q4], p2);
+      p0 = ffma2(xb, w0[2 * q4 + 1], p0); p1 = ffma2(xb, w1[2 * q4 + 1], p1); p2 = ffma2(xb, w2[2 * q4 + 1], p2);
     }
     __syncwarp();
     if (j == 0 && ((idx & (HG - 1)) == HG - 1 || idx + 1 == (unsigned)n)) mbar_arrive(&hin->gempty[g]);   // group free again
