@@ -76,8 +76,13 @@ SYMBOLS = {
 
 def load():
     if not os.path.exists(LIB_PATH):
-        raise ImportError("%s is missing: build it with `python -m hpmn_b200.build` (nvcc, sm_100a). "
-                          "There is no CPU fallback." % LIB_PATH)
+        # building the product is not a fallback: compile it in-tree when the toolchain is here, fail loudly otherwise
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError("%s is missing and could not be built (%s): run `python -m hpmn_b200.build` (nvcc, sm_100a). "
+                              "There is no CPU fallback." % (LIB_PATH, e))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol

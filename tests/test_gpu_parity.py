@@ -170,6 +170,39 @@ def test_gather_is_bit_exact_and_masks():
         lib.hpmn_destroy(ctx)
 
 
+@pytest.mark.parametrize("F,B,T", [(2, 1, 32), (2, 16, 256), (3, 5, 100)])
+def test_tcgen05_weight_gradient_kernel_matches_fp64(F, B, T):
+    """hpmn_debug_wgrad: the tcgen05 3xTF32 kernel and the fp32 FFMA kernel on the same random buffers, both against an
+    fp64 reference of dWg = [x|h_prev]^T da_g, dWc = [x|r*h_prev]^T da_c, db = column sums."""
+    import torch
+    from hpmn_b200 import _lib
+    from hpmn_b200.layout import param_layout
+    lib = _lib.lib()
+    ctx = C.c_void_p(); _lib.check(lib.hpmn_create(C.byref(ctx), 0))
+    sh = HpmnShape(B=B, T=T, F=F, E=16, H=32, periods=[2], L=2, hops=1, V=100)
+    lay, n = param_layout(sh)
+    c = sh.to_c()
+    M, D = B * T, F * 16
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(M, D, generator=g).cuda(); st = torch.rand(M, 128, generator=g).cuda(); da = torch.randn(M, 96, generator=g).cuda()
+    hprev = torch.zeros(M, 32, device="cuda"); hprev[1:] = st[:-1, :32]; hprev.view(B, T, 32)[:, 0] = 0
+    A = torch.cat([x, hprev], 1).double(); Arh = torch.cat([x, hprev * st[:, 32:64]], 1).double()
+    ref = {"User/GRU0/rnn/gru_cell/gates/kernel": (A.T @ da[:, :64].double()).cpu().numpy(),
+           "User/GRU0/rnn/gru_cell/candidate/kernel": (Arh.T @ da[:, 64:].double()).cpu().numpy(),
+           "User/GRU0/rnn/gru_cell/gates/bias": da[:, :64].double().sum(0).cpu().numpy(),
+           "User/GRU0/rnn/gru_cell/candidate/bias": da[:, 64:].double().sum(0).cpu().numpy()}
+    for use_tc in (0, 1):
+        grads = torch.zeros(n, device="cuda")
+        _lib.check(lib.hpmn_debug_wgrad(ctx, C.byref(c), 0, x.data_ptr(), D, st.data_ptr(), da.data_ptr(), grads.data_ptr(), use_tc, None), ctx)
+        torch.cuda.synchronize()
+        out = grads.cpu().numpy()
+        for name, r in ref.items():
+            off, shp = lay[name]
+            got = out[off: off + r.size].reshape(r.shape)
+            assert np.abs(got - r).max() <= 1e-5 * np.abs(r).max(), (use_tc, name)
+    lib.hpmn_destroy(ctx)
+
+
 def test_out_of_range_id_is_reported_by_host_entry():
     from hpmn_b200 import _lib
     sh = HpmnShape(B=2, T=8, F=2, E=16, H=32, periods=[2], L=2, hops=1, V=50)
