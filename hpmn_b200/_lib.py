@@ -66,6 +66,9 @@ SYMBOLS = {
     "hpmn_forward": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _OUT, _P, _P]),
     "hpmn_forward_backward": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _OUT, _P, _P]),
     "hpmn_step_host": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _I, _OUT, _P, _P]),
+    "hpmn_step_host_begin": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _I, _OUT, _P, _P]),
+    "hpmn_step_host_end": (_I, [_P, _SH, _OUT, _P]),
+    "hpmn_prefetch_host": (_I, [_P, _SH, _P, _P, _P]),
     "hpmn_clip_adam": (_I, [_P, _P, _P, _P, _P, _L, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "hpmn_debug_wgrad": (_I, [_P, _SH, _I, _P, _L, _P, _P, _P, _I, _P]),
     "hpmn_profile_enable": (_I, [_P, _I]),

@@ -28,6 +28,10 @@ struct hpmn_ctx {
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
+  // feed double buffering (hpmn_prefetch_host): copy stream, completion event, what is staged where
+  cudaStream_t copy;
+  cudaEvent_t ev_copy, ev_consumed[2];
+  const void* staged_ids; const void* staged_labels; int staged_slot, staged_B, cur_slot; bool consumed_valid[2];
   // row groups: the batch is cut into `groups` independent row ranges, each running its whole fwd+bwd chain on its own
   // stream, so one group's dense kernels fill the SMs while another group sits in its latency-bound recurrence
   int groups, group_min_rows;
@@ -103,12 +107,14 @@ static const char* kFamilyNames[HPMN_K_COUNT] = {"gather_fwd", "inproj_gemm", "r
 
 // ---- shared plumbing ------------------------------------------------------------------------
 // Workspace = header (whole-batch staging and per-row outputs) + G group regions (activations of one row group).
-struct Hdr { size_t ids, labels, pred, logit, w_hop0, memory, scalars, total; };
+struct Hdr { size_t ids, labels, ids2, labels2, pred, logit, w_hop0, memory, scalars, total; };   // ids2/labels2: prefetch slot
 static Hdr make_hdr(const Dims& d) {
   Hdr h; size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   h.ids = take((size_t)d.B * d.T * d.F * sizeof(int32_t));
   h.labels = take((size_t)d.B * sizeof(int32_t));
+  h.ids2 = take((size_t)d.B * d.T * d.F * sizeof(int32_t));
+  h.labels2 = take((size_t)d.B * sizeof(int32_t));
   h.pred = take((size_t)d.B * sizeof(float));
   h.logit = take((size_t)d.B * sizeof(float));
   h.w_hop0 = take((size_t)d.B * d.L * sizeof(float));
@@ -305,6 +311,11 @@ int hpmn_create(hpmn_ctx** out, int device) {
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_zero, cudaEventDisableTiming);
   ctx->zero_pending = false;
+  cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+  for (auto& ev : ctx->ev_consumed) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  ctx->staged_ids = nullptr; ctx->staged_labels = nullptr; ctx->staged_slot = 0; ctx->staged_B = 0; ctx->cur_slot = 0;
+  ctx->consumed_valid[0] = ctx->consumed_valid[1] = false;
   { const char* e_ov = getenv("HPMN_NO_OVERLAP"); ctx->overlap = !(e_ov && e_ov[0] == '1'); }
   for (auto& gs : ctx->gstream) cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking);
   for (auto& ev : ctx->ev_gdone) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -321,6 +332,8 @@ void hpmn_destroy(hpmn_ctx* ctx) {
   for (auto& ev : ctx->ev_fork) cudaEventDestroy(ev);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_zero);
+  cudaEventDestroy(ctx->ev_copy); for (auto& ev : ctx->ev_consumed) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->copy);
   cudaStreamDestroy(ctx->side);
   for (auto& gs : ctx->gstream) cudaStreamDestroy(gs);
   for (auto& ev : ctx->ev_gdone) cudaEventDestroy(ev);
@@ -640,7 +653,7 @@ int hpmn_forward_backward(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* 
   return check_launch(ctx, "hpmn_forward_backward");
 }
 
-int hpmn_step_host(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids_host,
+int hpmn_step_host_begin(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids_host,
                    const int32_t* labels_host, const float* params, const float* table, float* grads, float* dtable,
                    int zero_dtable, int with_backward, const hpmn_outputs* oh, void* workspace, void* stream) {
   Plan p; int rc = make_plan(ctx, s, workspace, p);
@@ -650,21 +663,65 @@ int hpmn_step_host(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, con
   hpmn_hyper h = hy ? *hy : default_hyper();
   cudaStream_t st = (cudaStream_t)stream;
   const Dims& d = p.d;
-  int32_t* ids = reinterpret_cast<int32_t*>(p.base + p.hdr.ids);
-  int32_t* labels = reinterpret_cast<int32_t*>(p.base + p.hdr.labels);
+  // two feed slots: a batch staged by hpmn_prefetch_host is consumed in place, otherwise it is copied on `st` into the
+  // slot no prefetch is pending for
+  int slot;
+  const bool staged = ctx->staged_ids == ids_host && ctx->staged_labels == labels_host && ctx->staged_B == d.B;
+  if (staged) {
+    slot = ctx->staged_slot;
+    CK(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+    ctx->staged_ids = nullptr; ctx->staged_labels = nullptr;
+  } else {
+    slot = ctx->staged_ids != nullptr ? 1 - ctx->staged_slot : 0;
+  }
+  int32_t* ids = reinterpret_cast<int32_t*>(p.base + (slot ? p.hdr.ids2 : p.hdr.ids));
+  int32_t* labels = reinterpret_cast<int32_t*>(p.base + (slot ? p.hdr.labels2 : p.hdr.labels));
   float* scalars = p.hf(p.hdr.scalars);
-  CK(cudaMemcpyAsync(ids, ids_host, (size_t)d.B * d.T * d.F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(labels, labels_host, (size_t)d.B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (!staged) {
+    CK(cudaMemcpyAsync(ids, ids_host, (size_t)d.B * d.T * d.F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(labels, labels_host, (size_t)d.B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  ctx->cur_slot = slot;
   rc = run_step(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, with_backward != 0, scalars, st);
   if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev_consumed[slot], st));       // the slot may be refilled once everything above has read it
+  ctx->consumed_valid[slot] = true;
   CK(cudaMemcpyAsync(oh->scalars, scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   rc = copy_outputs(ctx, p, oh, cudaMemcpyDeviceToHost, st);
   if (rc) return rc;
-  rc = check_launch(ctx, "hpmn_step_host");
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(st));
+  return check_launch(ctx, "hpmn_step_host");
+}
+
+int hpmn_step_host_end(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_outputs* oh, void* stream) {
+  if (!ctx || !s || !oh || !oh->scalars) return HPMN_EINVAL;
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
   if (oh->scalars[HPMN_S_IDERR] != 0.f)   // TF's GatherV2 raises InvalidArgumentError on CPU
     return fail(ctx, HPMN_EINVAL, "an id is outside [0, feature_size=%lld)", (long long)s->V);
+  return HPMN_OK;
+}
+
+int hpmn_step_host(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const int32_t* ids_host,
+                   const int32_t* labels_host, const float* params, const float* table, float* grads, float* dtable,
+                   int zero_dtable, int with_backward, const hpmn_outputs* oh, void* workspace, void* stream) {
+  int rc = hpmn_step_host_begin(ctx, s, hy, ids_host, labels_host, params, table, grads, dtable, zero_dtable, with_backward, oh,
+                                workspace, stream);
+  if (rc) return rc;
+  return hpmn_step_host_end(ctx, s, oh, stream);
+}
+
+int hpmn_prefetch_host(hpmn_ctx* ctx, const hpmn_shape* s, const int32_t* ids_host, const int32_t* labels_host, void* workspace) {
+  Plan p; int rc = make_plan(ctx, s, workspace, p);
+  if (rc) return rc;
+  if (!ids_host || !labels_host) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  const Dims& d = p.d;
+  const int slot = 1 - ctx->cur_slot;                   // the slot the most recent step is NOT reading
+  if (ctx->consumed_valid[slot]) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_consumed[slot], 0));
+  int32_t* ids = reinterpret_cast<int32_t*>(p.base + (slot ? p.hdr.ids2 : p.hdr.ids));
+  int32_t* labels = reinterpret_cast<int32_t*>(p.base + (slot ? p.hdr.labels2 : p.hdr.labels));
+  CK(cudaMemcpyAsync(ids, ids_host, (size_t)d.B * d.T * d.F * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy));
+  CK(cudaMemcpyAsync(labels, labels_host, (size_t)d.B * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy));
+  CK(cudaEventRecord(ctx->ev_copy, ctx->copy));
+  ctx->staged_ids = ids_host; ctx->staged_labels = labels_host; ctx->staged_slot = slot; ctx->staged_B = d.B;
   return HPMN_OK;
 }
 

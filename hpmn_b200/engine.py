@@ -162,18 +162,31 @@ class HpmnEngine:
 
     def step_host_pinned(self, with_backward: bool = True, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0,
                          zero_dtable: bool = True, B: Optional[int] = None, h_ids: Optional[torch.Tensor] = None,
-                         h_labels: Optional[torch.Tensor] = None):
+                         h_labels: Optional[torch.Tensor] = None, prefetch_next=None):
         """Same, with the feed already in pinned host memory: self.h_ids / self.h_labels (first B rows, contiguous)
-        or caller-owned pinned int32 tensors."""
+        or caller-owned pinned int32 tensors.  prefetch_next = (pinned ids, pinned labels) of the NEXT batch: its H2D copy
+        is queued on the library's copy stream while this step computes (double-buffered feed)."""
         B = self.shape.B if B is None else B
         h_ids = self.h_ids if h_ids is None else h_ids
         h_labels = self.h_labels if h_labels is None else h_labels
         hy = self._hyper(keep_prob, seed, loss_batch)
-        _lib.check(self.lib.hpmn_step_host(self.ctx, C.byref(self._cshape(B)), C.byref(hy), _ptr(h_ids),
-                                           _ptr(h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
-                                           _ptr(self.dtable), int(zero_dtable), int(with_backward),
-                                           C.byref(self._out_host), _ptr(self.workspace), self._stream()), self.ctx)
+        cs = self._cshape(B)
+        st = self._stream()
+        _lib.check(self.lib.hpmn_step_host_begin(self.ctx, C.byref(cs), C.byref(hy), _ptr(h_ids),
+                                                 _ptr(h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
+                                                 _ptr(self.dtable), int(zero_dtable), int(with_backward),
+                                                 C.byref(self._out_host), _ptr(self.workspace), st), self.ctx)
+        if prefetch_next is not None:
+            self.prefetch_host(prefetch_next[0], prefetch_next[1], B)
+        _lib.check(self.lib.hpmn_step_host_end(self.ctx, C.byref(cs), C.byref(self._out_host), st), self.ctx)
         return self.h_scalars.numpy(), self.h_pred.numpy()[:B]
+
+    def prefetch_host(self, h_ids: torch.Tensor, h_labels: torch.Tensor, B: Optional[int] = None):
+        """Start the H2D copy of the NEXT batch (pinned int32 tensors) on the library's copy stream; the following
+        step_host_pinned(..., h_ids=, h_labels=) with the same tensors consumes it without copying again."""
+        B = self.shape.B if B is None else B
+        _lib.check(self.lib.hpmn_prefetch_host(self.ctx, C.byref(self._cshape(B)), _ptr(h_ids), _ptr(h_labels),
+                                               _ptr(self.workspace)), self.ctx)
 
     def apply_gradients(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, clip: float = 1.0):
         """clip_by_value(g,-1,1) + dense Adam over [dense params | table] (hpmn.py:209-214; the clip densifies the

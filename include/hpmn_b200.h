@@ -152,6 +152,20 @@ int hpmn_step_host(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_
                    float* dtable, int zero_dtable, int with_backward, const hpmn_outputs* out_host,
                    void* workspace, void* stream);
 
+/* The same call split in two so that other work can be queued between enqueue and wait: _begin enqueues H2D + compute +
+ * D2H and returns immediately, _end synchronises the stream and reports an out-of-range id. */
+int hpmn_step_host_begin(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids_host,
+                         const int32_t* labels_host, const float* params, const float* table, float* grads,
+                         float* dtable, int zero_dtable, int with_backward, const hpmn_outputs* out_host,
+                         void* workspace, void* stream);
+int hpmn_step_host_end(hpmn_ctx*, const hpmn_shape*, const hpmn_outputs* out_host, void* stream);
+
+/* Optional double buffering of the feed: start the H2D copy of the NEXT batch (pinned host memory) on the library's copy
+ * stream while the current step computes.  A following hpmn_step_host() called with the same ids_host / labels_host pointers
+ * and shape uses the staged copy instead of copying again.  Call it between hpmn_step_host_begin and hpmn_step_host_end of the
+ * current step.  The host buffers must stay untouched until the consuming call returns. */
+int hpmn_prefetch_host(hpmn_ctx*, const hpmn_shape*, const int32_t* ids_host, const int32_t* labels_host, void* workspace);
+
 /* ---- update step: clip_by_value(g,-1,1) + dense Adam (code/hpmn.py:209-214) ---------------- */
 /* var, m, v updated in place over n floats; t = 1-based step; TF1.4 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t) */
 int hpmn_clip_adam(hpmn_ctx*, float* var, const float* grad, float* m, float* v, int64_t n, int64_t t,

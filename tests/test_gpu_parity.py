@@ -216,6 +216,38 @@ def test_out_of_range_id_is_reported_by_host_entry():
     eng.close()
 
 
+def test_prefetched_feed_gives_identical_results():
+    """hpmn_prefetch_host (double-buffered H2D on the copy stream) must not change any result, whatever the order of
+    prefetched and non-prefetched steps."""
+    import torch
+    sh = HpmnShape(B=12, T=16, F=2, E=16, H=32, periods=[2, 2], L=3, hops=2, V=90)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    batches = []
+    for k in range(4):
+        ids, labels = O.synthetic_batch(osh, seed=100 + k)
+        batches.append((torch.from_numpy(ids).pin_memory(), torch.from_numpy(labels).pin_memory()))
+    eng = _engine(sh, params, table, 1e-3)
+    ref = []
+    for ids, labels in batches:                       # plain path
+        _, pred = eng.step_host_pinned(True, 1.0, 0, 0, True, sh.B, ids, labels)
+        ref.append((pred.copy(), eng.grads.clone(), eng.h_scalars.numpy().copy()))
+    eng.prefetch_host(batches[0][0], batches[0][1])
+    for k, (ids, labels) in enumerate(batches):       # every feed staged one step ahead
+        nxt = batches[k + 1] if k + 1 < len(batches) else None
+        _, pred = eng.step_host_pinned(True, 1.0, 0, 0, True, sh.B, ids, labels, prefetch_next=nxt)
+        assert np.array_equal(pred, ref[k][0])
+        np.testing.assert_allclose(eng.h_scalars.numpy()[:3], ref[k][2][:3], rtol=1e-6)
+        assert float((eng.grads - ref[k][1]).abs().max()) <= 1e-6 * float(ref[k][1].abs().max()) + 1e-9
+    # a stale prefetch (never consumed) followed by an unrelated plain step
+    eng.prefetch_host(batches[3][0], batches[3][1])
+    _, pred = eng.step_host_pinned(True, 1.0, 0, 0, True, sh.B, batches[1][0], batches[1][1])
+    assert np.array_equal(pred, ref[1][0])
+    _, pred = eng.step_host_pinned(True, 1.0, 0, 0, True, sh.B, batches[3][0], batches[3][1])
+    assert np.array_equal(pred, ref[3][0])
+    eng.close()
+
+
 def test_smaller_batch_reuses_engine_and_dropout_is_deterministic():
     import torch
     sh = HpmnShape(B=16, T=12, F=2, E=16, H=32, periods=[2, 3], L=3, hops=2, V=80)
