@@ -187,11 +187,11 @@ static void dense_gemm(hpmn_ctx* ctx, const Launch& L, const float* A, int64_t l
 
 // memory forward: pack + per layer (projection GEMM, recurrence)
 static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool packed = false) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
-  { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
+  if (!packed) { Bracket b(ctx, st, HPMN_K_MISC); launch_pack(L, d, p.pl, p.pk, params, pw, st); }
   if (ctx->use_wave && ctx->wave_now && d.L <= 10) {
     // layer-0 input projections (dense, tensor cores), then every layer of every sample as one wavefront kernel
     { Bracket b(ctx, st, HPMN_K_INPROJ);
@@ -498,16 +498,19 @@ int hpmn_head_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, cons
 // ---- whole path -------------------------------------------------------------------------------
 // forward chain of one row group (rows [p.row0, p.row0 + p.d.B)) on stream st
 static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hpmn_hyper& hy, const int32_t* ids,
-                     const int32_t* labels, const float* params, const float* table, float* scalars, cudaStream_t st) {
+                     const int32_t* labels, const float* params, const float* table, float* scalars, bool side_ok,
+                     cudaStream_t st) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   const int r0 = p.row0;
   float* x = p.f(p.wl.x);
   float* memory = p.hf(p.hdr.memory) + (int64_t)r0 * d.L * d.H;
+  const bool ov = side_ok;      // run_step already queued the weight repacking on the side stream (event ev_join)
   { Bracket b(ctx, st, HPMN_K_GATHER);
     launch_gather_fwd(L, d, s->mask_id0 != 0, s->front_pad, s->V, ids + (int64_t)r0 * d.T * d.F, table, x,
                       scalars + HPMN_S_IDERR, st); }
-  run_memory_fwd(ctx, p, x, params, memory, st);
+  if (ov) cudaStreamWaitEvent(st, ctx->ev_join, 0);
+  run_memory_fwd(ctx, p, x, params, memory, st, ov);
   { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
     launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L,
                     scalars, p.att(), st); }
@@ -562,6 +565,15 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   int G = ctx->profile ? 1 : ctx->groups;
   while (G > 1 && d.B / G < ctx->group_min_rows) --G;
   ctx->zero_pending = false;
+  // the weight repacking does not depend on the gather: it runs beside it on the side stream (ahead of the table-gradient
+  // zeroing queued there below) and is joined in front of the projection GEMM
+  const bool side_pack = G == 1 && ctx->overlap && !ctx->profile;
+  if (side_pack) {
+    CK(cudaEventRecord(ctx->ev_fork[0], st));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork[0], 0));
+    launch_pack(L, d, p.pl, p.pk, params, p.f(p.wl.pw), ctx->side);
+    CK(cudaEventRecord(ctx->ev_join, ctx->side));
+  }
   { Bracket b(ctx, st, HPMN_K_MISC);
     CK(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
     if (with_backward) {
@@ -581,7 +593,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
       }
     } }
   if (G == 1) {
-    fwd_rows(ctx, p, s, hy, ids, labels, params, table, scalars, st);
+    fwd_rows(ctx, p, s, hy, ids, labels, params, table, scalars, side_pack, st);
     if (with_backward) bwd_rows(ctx, p, s, hy, ids, labels, params, grads, dtable, true, st);
   } else {
     CK(cudaEventRecord(ctx->ev_gstart, st));
@@ -592,7 +604,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
       const Plan gp = group_plan(p, s, g, G, row0, rows);
       cudaStream_t gs = ctx->gstream[g];
       CK(cudaStreamWaitEvent(gs, ctx->ev_gstart, 0));
-      fwd_rows(ctx, gp, s, hy, ids, labels, params, table, scalars, gs);
+      fwd_rows(ctx, gp, s, hy, ids, labels, params, table, scalars, false, gs);
       if (with_backward) bwd_rows(ctx, gp, s, hy, ids, labels, params, grads, dtable, false, gs);
       CK(cudaEventRecord(ctx->ev_gdone[g], gs));
       CK(cudaStreamWaitEvent(st, ctx->ev_gdone[g], 0));

@@ -26,19 +26,49 @@ struct AttnArgs {
 };
 
 constexpr int NT = 256;               // threads per CTA
-constexpr int A1S = ATT1 + 1;         // padded row strides of the staged score-MLP weights (bank-conflict free
-constexpr int A2S = ATT2 + 1;         //   for both the forward (column) and the backward (row) access pattern)
+// Row strides of the staged score-MLP weights: 16-byte aligned (float4 staging stores) and an odd number of float4s, so
+// that both access patterns are bank-conflict free -- forward: scalar loads, lanes over the output unit (column);
+// backward: float4 loads along a row, lanes over the row.
+constexpr int A1S = ATT1 + 4;
+constexpr int A2S = ATT2 + 4;
+constexpr int PF1 = (4 * HP * ATT1 / 4 + NT - 1) / NT;   // float4s of A1 per thread (10)
+constexpr int PF2 = (ATT1 * ATT2 / 4 + NT - 1) / NT;     // float4s of A2 per thread (4)
 
-// stage one hop's score-MLP weights in shared memory: A1 [4H,80] -> [4H][81], A2 [80,40] -> [80][41], A3 [40]
-__device__ __forceinline__ void stage_weights(const float* __restrict__ P, const AttnArgs& a, int hop, int H4, float* sA1,
-                                              float* sA2, float* sA3, float* sB1, float* sB2) {
-  const int tid = threadIdx.x;
-  for (int e = tid; e < H4 * ATT1; e += NT) sA1[(e / ATT1) * A1S + e % ATT1] = __ldg(P + a.A1[hop] + e);
-  for (int e = tid; e < ATT1 * ATT2; e += NT) sA2[(e / ATT2) * A2S + e % ATT2] = __ldg(P + a.A2[hop] + e);
-  if (tid < ATT2) sA3[tid] = __ldg(P + a.A3[hop] + tid);
-  if (tid < ATT1) sB1[tid] = __ldg(P + a.a1[hop] + tid);
-  if (tid < ATT2) sB2[tid] = __ldg(P + a.a2[hop] + tid);
-}
+// One hop's score-MLP weights on their way from L2 to shared memory.  fetch() only issues the loads, so the hop that
+// is being computed hides their latency; put() lands them once every reader of the previous weights has passed a barrier.
+struct WPref {
+  float4 a1[PF1], a2[PF2];
+  float a3, b1, b2;
+  __device__ __forceinline__ void fetch(const float* __restrict__ P, const AttnArgs& a, int hop, int H4) {
+    const int tid = threadIdx.x;
+    const float4* g1 = reinterpret_cast<const float4*>(P + a.A1[hop]);
+    const float4* g2 = reinterpret_cast<const float4*>(P + a.A2[hop]);
+    const int n1 = H4 * (ATT1 / 4);
+#pragma unroll
+    for (int q = 0; q < PF1; ++q) { const int e = tid + NT * q; if (e < n1) a1[q] = __ldg(g1 + e); }
+#pragma unroll
+    for (int q = 0; q < PF2; ++q) { const int e = tid + NT * q; if (e < ATT1 * ATT2 / 4) a2[q] = __ldg(g2 + e); }
+    a3 = tid < ATT2 ? __ldg(P + a.A3[hop] + tid) : 0.f;
+    b1 = tid < ATT1 ? __ldg(P + a.a1[hop] + tid) : 0.f;
+    b2 = tid < ATT2 ? __ldg(P + a.a2[hop] + tid) : 0.f;
+  }
+  __device__ __forceinline__ void put(int H4, float* sA1, float* sA2, float* sA3, float* sB1, float* sB2) const {
+    const int tid = threadIdx.x;
+    const int n1 = H4 * (ATT1 / 4);
+#pragma unroll
+    for (int q = 0; q < PF1; ++q) {
+      const int e = tid + NT * q;
+      if (e < n1) *reinterpret_cast<float4*>(sA1 + (e / (ATT1 / 4)) * A1S + (e % (ATT1 / 4)) * 4) = a1[q];
+    }
+#pragma unroll
+    for (int q = 0; q < PF2; ++q) {
+      const int e = tid + NT * q;
+      if (e < ATT1 * ATT2 / 4) *reinterpret_cast<float4*>(sA2 + (e / (ATT2 / 4)) * A2S + (e % (ATT2 / 4)) * 4) = a2[q];
+    }
+    if (tid < ATT2) { sA3[tid] = a3; sB2[tid] = b2; }
+    if (tid < ATT1) sB1[tid] = b1;
+  }
+};
 
 // covariance pieces shared by fwd and bwd: centred memory mean per slot, off-diagonal C, Frobenius norm
 __device__ __forceinline__ float covreg_block(const float (*sM)[HP], float* sMean, float (*sC)[ML], float* sRed, int L,
@@ -69,7 +99,7 @@ __device__ __forceinline__ float covreg_block(const float (*sM)[HP], float* sMea
   return sqrtf(tot);
 }
 
-// dynamic shared memory carve-up (floats)
+// dynamic shared memory carve-up (floats; every block starts on a 16-byte boundary)
 struct AttSmem {
   float *A1, *A2, *A3, *B1, *B2, *Inp, *Z1, *Z2;
   __device__ AttSmem(float* base, int H4) {
@@ -79,31 +109,52 @@ struct AttSmem {
   static size_t bytes(int H4) { return sizeof(float) * (size_t)(H4 * A1S + ATT1 * A2S + 2 * ATT2 + ATT1 + ML * 4 * HP + ML * ATT1 + ML * ATT2); }
 };
 
-__global__ void __launch_bounds__(NT)
+constexpr int QS = HP + 1;             // padded row stride of the staged Wq / Hmap (column and row access conflict free)
+
+// Wq [D,H] and Hmap [H,H] -> shared memory (coalesced; rows padded to QS)
+__device__ __forceinline__ void stage_qmaps(const float* __restrict__ P, const AttnArgs& a, float* sWq, float* sHm) {
+  const int tid = threadIdx.x, H = a.H, D = a.D;
+  for (int e = tid; e < D * H; e += NT) sWq[(e / H) * QS + e % H] = __ldg(P + a.Wq + e);
+  for (int e = tid; e < H * H; e += NT) sHm[(e / H) * QS + e % H] = __ldg(P + a.Hmap + e);
+}
+
+__global__ void __launch_bounds__(NT, 2)
 attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ __align__(16) float dsm[];
-  __shared__ float sM[ML][HP];
+  __shared__ __align__(16) float sM[ML][HP];
   __shared__ float sC[ML][ML];
   __shared__ float sMean[ML], sRed[NT / 32], sS[ML], sW[ML];
-  __shared__ float sLast[MD], sQ[HP], sQn[HP];
+  __shared__ __align__(16) float sLast[MD];
+  __shared__ __align__(16) float sQ[HP];
+  __shared__ float sQn[HP];
+  __shared__ float sWq[MD * QS], sHm[HP * QS];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
   AttSmem S(dsm, H4);
-  const float* P = a.params;
+  const float* __restrict__ P = a.params;
+  WPref wp;
+  wp.fetch(P, a, 0, H4);
   for (int e = tid; e < L * H; e += NT) sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e);
   for (int e = tid; e < D; e += NT) sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
-  stage_weights(P, a, 0, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
+  const float bqv = tid < H ? __ldg(P + a.bq + tid) : 0.f;
+  stage_qmaps(P, a, sWq, sHm);
+  wp.put(H4, S.A1, S.A2, S.A3, S.B1, S.B2);
   __syncthreads();
   const float nrm = covreg_block(sM, sMean, sC, sRed, L, H);          // hpmn.py:161-170
   if (tid == 0) atomicAdd(a.scalars + HPMN_S_COVREG, nrm);
   if (tid < H) {                                                       // query = dense(last, H), hpmn.py:173
-    float q = __ldg(P + a.bq + tid);
-    for (int i = 0; i < D; ++i) q = fmaf(sLast[i], __ldg(P + a.Wq + (int64_t)i * H + tid), q);
+    float q0 = bqv, q1 = 0.f;
+    int i = 0;
+    for (; i + 2 <= D; i += 2) { q0 = fmaf(sLast[i], sWq[i * QS + tid], q0); q1 = fmaf(sLast[i + 1], sWq[(i + 1) * QS + tid], q1); }
+    if (i < D) q0 = fmaf(sLast[i], sWq[i * QS + tid], q0);
+    const float q = q0 + q1;
     sQ[tid] = q;
     a.ws.q[(int64_t)b * H + tid] = q;
   }
   __syncthreads();
+  const int npair = (L + 1) >> 1;
   for (int hop = 0; hop < a.hops; ++hop) {
+    if (hop + 1 < a.hops) wp.fetch(P, a, hop + 1, H4);                // lands after this hop's last weight read
     float* ginp = a.ws.inp + ((int64_t)hop * B + b) * L * H4;
     for (int e = tid; e < L * H4; e += NT) {                           // hpmn.py:135-136
       const int l = e / H4, c = e % H4, part = c / H, j = c % H;
@@ -114,36 +165,49 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
     }
     __syncthreads();
     {                                                                  // fc1 (4H -> 80, relu), hpmn.py:137
+      // thread = (slot pair, unit): one weight load feeds two slots, inputs come as broadcast float4s
       float* gz1 = a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1;
-      for (int w = tid; w < L * ATT1; w += NT) {                       // one (slot, unit) per thread
-        const int l = w / ATT1, o = w % ATT1;
-        const float* in = S.Inp + l * H4;
-        float acc0 = S.B1[o], acc1 = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < H4; i += 2) {
-          acc0 = fmaf(in[i], S.A1[i * A1S + o], acc0);
-          acc1 = fmaf(in[i + 1], S.A1[(i + 1) * A1S + o], acc1);
+      const int o = tid % ATT1;
+      for (int lp = tid < (NT / ATT1) * ATT1 ? tid / ATT1 : npair; lp < npair; lp += NT / ATT1) {
+        const int l0 = 2 * lp, l1 = min(2 * lp + 1, L - 1);
+        const float4* in0 = reinterpret_cast<const float4*>(S.Inp + l0 * H4);
+        const float4* in1 = reinterpret_cast<const float4*>(S.Inp + l1 * H4);
+        const float* wcol = S.A1 + o;
+        float p0 = S.B1[o], p1 = 0.f, r0 = p0, r1 = 0.f;
+#pragma unroll 4
+        for (int i4 = 0; i4 < H; ++i4) {                               // H4 / 4 float4s
+          const float4 x = in0[i4], y = in1[i4];
+          const float w0 = wcol[(4 * i4) * A1S], w1 = wcol[(4 * i4 + 1) * A1S], w2 = wcol[(4 * i4 + 2) * A1S],
+                      w3 = wcol[(4 * i4 + 3) * A1S];
+          p0 = fmaf(x.x, w0, p0); p1 = fmaf(x.y, w1, p1); p0 = fmaf(x.z, w2, p0); p1 = fmaf(x.w, w3, p1);
+          r0 = fmaf(y.x, w0, r0); r1 = fmaf(y.y, w1, r1); r0 = fmaf(y.z, w2, r0); r1 = fmaf(y.w, w3, r1);
         }
-        const float v = fmaxf(acc0 + acc1, 0.f);
-        S.Z1[l * ATT1 + o] = v;
-        gz1[w] = v;
+        const float v0 = fmaxf(p0 + p1, 0.f), v1 = fmaxf(r0 + r1, 0.f);
+        S.Z1[l0 * ATT1 + o] = v0; gz1[l0 * ATT1 + o] = v0;
+        if (2 * lp + 1 < L) { S.Z1[l1 * ATT1 + o] = v1; gz1[l1 * ATT1 + o] = v1; }
       }
     }
     __syncthreads();
     {                                                                  // fc2 (80 -> 40, relu), hpmn.py:138
       float* gz2 = a.ws.z2 + ((int64_t)hop * B + b) * L * ATT2;
-      for (int w = tid; w < L * ATT2; w += NT) {
-        const int l = w / ATT2, o = w % ATT2;
-        const float* in = S.Z1 + l * ATT1;
-        float acc0 = S.B2[o], acc1 = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < ATT1; i += 2) {
-          acc0 = fmaf(in[i], S.A2[i * A2S + o], acc0);
-          acc1 = fmaf(in[i + 1], S.A2[(i + 1) * A2S + o], acc1);
+      const int o = tid % ATT2;
+      for (int lp = tid < (NT / ATT2) * ATT2 ? tid / ATT2 : npair; lp < npair; lp += NT / ATT2) {
+        const int l0 = 2 * lp, l1 = min(2 * lp + 1, L - 1);
+        const float4* in0 = reinterpret_cast<const float4*>(S.Z1 + l0 * ATT1);
+        const float4* in1 = reinterpret_cast<const float4*>(S.Z1 + l1 * ATT1);
+        const float* wcol = S.A2 + o;
+        float p0 = S.B2[o], p1 = 0.f, r0 = p0, r1 = 0.f;
+#pragma unroll 4
+        for (int i4 = 0; i4 < ATT1 / 4; ++i4) {
+          const float4 x = in0[i4], y = in1[i4];
+          const float w0 = wcol[(4 * i4) * A2S], w1 = wcol[(4 * i4 + 1) * A2S], w2 = wcol[(4 * i4 + 2) * A2S],
+                      w3 = wcol[(4 * i4 + 3) * A2S];
+          p0 = fmaf(x.x, w0, p0); p1 = fmaf(x.y, w1, p1); p0 = fmaf(x.z, w2, p0); p1 = fmaf(x.w, w3, p1);
+          r0 = fmaf(y.x, w0, r0); r1 = fmaf(y.y, w1, r1); r0 = fmaf(y.z, w2, r0); r1 = fmaf(y.w, w3, r1);
         }
-        const float v = fmaxf(acc0 + acc1, 0.f);
-        S.Z2[l * ATT2 + o] = v;
-        gz2[w] = v;
+        const float v0 = fmaxf(p0 + p1, 0.f), v1 = fmaxf(r0 + r1, 0.f);
+        S.Z2[l0 * ATT2 + o] = v0; gz2[l0 * ATT2 + o] = v0;
+        if (2 * lp + 1 < L) { S.Z2[l1 * ATT2 + o] = v1; gz2[l1 * ATT2 + o] = v1; }
       }
     }
     __syncthreads();
@@ -165,16 +229,18 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
         a.ws.w[((int64_t)hop * B + b) * L + lane] = w;
         if (hop == 0) a.w_hop0[(int64_t)b * L + lane] = w;             // weights[0], hpmn.py:182
       }
+      __syncwarp();
+      if (lane < H) {                                                  // query = query @ H + read, hpmn.py:179
+        float qn = 0.f, qm = 0.f;
+        for (int l = 0; l < L; ++l) qn = fmaf(sW[l], sM[l][lane], qn);   // hpmn.py:143-144
+        for (int i = 0; i < H; ++i) qm = fmaf(sQ[i], sHm[i * QS + lane], qm);
+        qn += qm;
+        sQn[lane] = qn;
+        a.ws.q[((int64_t)(hop + 1) * B + b) * H + lane] = qn;
+      }
     }
-    __syncthreads();
-    if (tid < H) {                                                     // query = query @ H + read, hpmn.py:179
-      float qn = 0.f;
-      for (int l = 0; l < L; ++l) qn = fmaf(sW[l], sM[l][tid], qn);    // hpmn.py:143-144
-      for (int i = 0; i < H; ++i) qn = fmaf(sQ[i], __ldg(P + a.Hmap + (int64_t)i * H + tid), qn);
-      sQn[tid] = qn;
-      a.ws.q[((int64_t)(hop + 1) * B + b) * H + tid] = qn;
-    }
-    if (hop + 1 < a.hops) stage_weights(P, a, hop + 1, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
+    // every thread is past its last read of this hop's weights (barrier after fc3): land the next hop's
+    if (hop + 1 < a.hops) wp.put(H4, S.A1, S.A2, S.A3, S.B1, S.B2);
     __syncthreads();
     if (tid < H) sQ[tid] = sQn[tid];
     __syncthreads();
@@ -183,32 +249,34 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
   for (int e = tid; e < D; e += NT) a.repre[(int64_t)b * (H + D) + H + e] = sLast[e];
 }
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ __align__(16) float dsm[];
-  __shared__ float sM[ML][HP];
+  __shared__ __align__(16) float sM[ML][HP];
   __shared__ float sDm[ML][HP];
   __shared__ float sT[ML][HP];
   __shared__ float sC[ML][ML];
   __shared__ float sMean[ML], sRed[NT / 32], sW[ML], sDw[ML], sDs[ML], sMean2[ML];
-  __shared__ float sLast[MD], sDlast[MD], sQ[HP], sDq[HP], sDqin[HP];
+  __shared__ __align__(16) float sDlast[MD], sQ[HP], sDq[HP], sDqin[HP];
+  __shared__ float sWq[MD * QS], sHm[HP * QS];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
   AttSmem S(dsm, H4);                       // S.Inp holds d(inp); S.Z1 / S.Z2 hold z then dz
-  const float* P = a.params;
+  const float* __restrict__ P = a.params;
+  WPref wp;
+  wp.fetch(P, a, a.hops - 1, H4);
   for (int e = tid; e < L * H; e += NT) { sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e); sDm[e / H][e % H] = 0.f; }
-  for (int e = tid; e < D; e += NT) {
-    sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
-    sDlast[e] = __ldg(a.drepre + (int64_t)b * (H + D) + H + e);
-  }
+  for (int e = tid; e < D; e += NT) sDlast[e] = __ldg(a.drepre + (int64_t)b * (H + D) + H + e);
+  stage_qmaps(P, a, sWq, sHm);
   if (tid < H) {
     const float g = __ldg(a.drepre + (int64_t)b * (H + D) + tid);
     sDq[tid] = g;
     a.ws.dq[((int64_t)a.hops * B + b) * H + tid] = g;
   }
-  __syncthreads();
   for (int hop = a.hops - 1; hop >= 0; --hop) {
-    stage_weights(P, a, hop, H4, S.A1, S.A2, S.A3, S.B1, S.B2);
+    __syncthreads();                        // previous hop's readers of the staged weights / sDq writers are done
+    wp.put(H4, S.A1, S.A2, S.A3, S.B1, S.B2);
+    if (hop > 0) wp.fetch(P, a, hop - 1, H4);
     if (tid < H) sQ[tid] = __ldg(a.ws.q + ((int64_t)hop * B + b) * H + tid);
     if (tid < L) sW[tid] = __ldg(a.ws.w + ((int64_t)hop * B + b) * L + tid);
     for (int e = tid; e < L * ATT1; e += NT) S.Z1[e] = __ldg(a.ws.z1 + ((int64_t)hop * B + b) * L * ATT1 + e);
@@ -216,9 +284,9 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     __syncthreads();
     // q_out = q_in @ Hmap + read ;  read = sum_l w_l m_l
     if (tid < H) {
-      float s = 0.f;
-      for (int j = 0; j < H; ++j) s = fmaf(sDq[j], __ldg(P + a.Hmap + (int64_t)tid * H + j), s);
-      sDqin[tid] = s;
+      float s0 = 0.f;                                                  // d q_in = d q_out @ Hmap^T: row tid of Hmap
+      for (int j = 0; j < H; ++j) s0 = fmaf(sDq[j], sHm[tid * QS + j], s0);
+      sDqin[tid] = s0;
     }
     for (int l = warp; l < L; l += NT / 32) {
       const float dq = lane < H ? sDq[lane] : 0.f;
@@ -246,34 +314,55 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
       a.ws.dz2[((int64_t)hop * B + b) * L * ATT2 + e] = v;
     }
     __syncthreads();
-    // dz1[l][o] = (sum_o2 dz2[l][o2] A2[o][o2]) (z1 > 0)
-    for (int w = tid; w < L * ATT1; w += NT) {
-      const int l = w / ATT1, o = w % ATT1;
-      const float* dz2 = S.Z2 + l * ATT2;
-      const float* row = S.A2 + o * A2S;
-      float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-      for (int o2 = 0; o2 < ATT2; o2 += 2) {
-        acc0 = fmaf(dz2[o2], row[o2], acc0);
-        acc1 = fmaf(dz2[o2 + 1], row[o2 + 1], acc1);
+    // dz1[l][o] = (sum_o2 dz2[l][o2] A2[o][o2]) (z1 > 0): thread = (slot pair, unit o), row o of A2 as float4s
+    {
+      const int npair = (L + 1) >> 1;
+      const int o = tid % ATT1;
+      float* gdz1 = a.ws.dz1 + ((int64_t)hop * B + b) * L * ATT1;
+      const float4* row = reinterpret_cast<const float4*>(S.A2 + o * A2S);
+      for (int lp = tid < (NT / ATT1) * ATT1 ? tid / ATT1 : npair; lp < npair; lp += NT / ATT1) {
+        const int l0 = 2 * lp, l1 = min(2 * lp + 1, L - 1);
+        const float4* d0 = reinterpret_cast<const float4*>(S.Z2 + l0 * ATT2);
+        const float4* d1 = reinterpret_cast<const float4*>(S.Z2 + l1 * ATT2);
+        float p0 = 0.f, p1 = 0.f, r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < ATT2 / 4; ++q) {
+          const float4 w = row[q], x = d0[q], y = d1[q];
+          p0 = fmaf(x.x, w.x, p0); p1 = fmaf(x.y, w.y, p1); p0 = fmaf(x.z, w.z, p0); p1 = fmaf(x.w, w.w, p1);
+          r0 = fmaf(y.x, w.x, r0); r1 = fmaf(y.y, w.y, r1); r0 = fmaf(y.z, w.z, r0); r1 = fmaf(y.w, w.w, r1);
+        }
+        // Z1 is only overwritten after the barrier below (other threads still read nothing of it here: own elements only)
+        const float v0 = S.Z1[l0 * ATT1 + o] > 0.f ? p0 + p1 : 0.f;
+        S.Z1[l0 * ATT1 + o] = v0; gdz1[l0 * ATT1 + o] = v0;
+        if (2 * lp + 1 < L) {
+          const float v1 = S.Z1[l1 * ATT1 + o] > 0.f ? r0 + r1 : 0.f;
+          S.Z1[l1 * ATT1 + o] = v1; gdz1[l1 * ATT1 + o] = v1;
+        }
       }
-      const float v = S.Z1[w] > 0.f ? acc0 + acc1 : 0.f;
-      S.Z1[w] = v;                                                     // own element only: no hazard
-      a.ws.dz1[((int64_t)hop * B + b) * L * ATT1 + w] = v;
     }
     __syncthreads();
-    // dinp[l][i] = sum_o dz1[l][o] A1[i][o]
-    for (int w = tid; w < L * H4; w += NT) {
-      const int l = w / H4, i = w % H4;
-      const float* dz1 = S.Z1 + l * ATT1;
-      const float* row = S.A1 + i * A1S;
-      float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-      for (int o = 0; o < ATT1; o += 2) {
-        acc0 = fmaf(dz1[o], row[o], acc0);
-        acc1 = fmaf(dz1[o + 1], row[o + 1], acc1);
+    // dinp[l][i] = sum_o dz1[l][o] A1[i][o]: thread = (slot parity, input unit i), row i of A1 as float4s, 3 slots at a time
+    {
+      const int i = tid % H4;
+      const float4* row = reinterpret_cast<const float4*>(S.A1 + i * A1S);
+      const int nth = NT / H4;                                         // slot interleave (2 at H = 32)
+      for (int lb = tid < nth * H4 ? tid / H4 : L; lb < L; lb += 3 * nth) {
+        const int l0 = lb, l1 = min(lb + nth, L - 1), l2 = min(lb + 2 * nth, L - 1);
+        const float4* d0 = reinterpret_cast<const float4*>(S.Z1 + l0 * ATT1);
+        const float4* d1 = reinterpret_cast<const float4*>(S.Z1 + l1 * ATT1);
+        const float4* d2 = reinterpret_cast<const float4*>(S.Z1 + l2 * ATT1);
+        float p0 = 0.f, p1 = 0.f, r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll 5
+        for (int q = 0; q < ATT1 / 4; ++q) {
+          const float4 w = row[q], x = d0[q], y = d1[q], z = d2[q];
+          p0 = fmaf(x.x, w.x, p0); p1 = fmaf(x.y, w.y, p1); p0 = fmaf(x.z, w.z, p0); p1 = fmaf(x.w, w.w, p1);
+          r0 = fmaf(y.x, w.x, r0); r1 = fmaf(y.y, w.y, r1); r0 = fmaf(y.z, w.z, r0); r1 = fmaf(y.w, w.w, r1);
+          t0 = fmaf(z.x, w.x, t0); t1 = fmaf(z.y, w.y, t1); t0 = fmaf(z.z, w.z, t0); t1 = fmaf(z.w, w.w, t1);
+        }
+        S.Inp[l0 * H4 + i] = p0 + p1;
+        if (lb + nth < L) S.Inp[l1 * H4 + i] = r0 + r1;
+        if (lb + 2 * nth < L) S.Inp[l2 * H4 + i] = t0 + t1;
       }
-      S.Inp[l * H4 + i] = acc0 + acc1;
     }
     __syncthreads();
     // inp = [q, m, q-m, q*m]
@@ -291,12 +380,12 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
       sDq[tid] = g;                       // every other reader of sDq finished before the last barrier
       a.ws.dq[((int64_t)hop * B + b) * H + tid] = g;
     }
-    __syncthreads();
   }
+  __syncthreads();
   // q0 = last @ Wq + bq
   for (int i = tid; i < D; i += NT) {
     float s = sDlast[i];
-    for (int j = 0; j < H; ++j) s = fmaf(sDq[j], __ldg(P + a.Wq + (int64_t)i * H + j), s);
+    for (int j = 0; j < H; ++j) s = fmaf(sDq[j], sWq[i * QS + j], s);
     a.dlast[(int64_t)b * D + i] = s;
   }
   // covreg adjoint: d||offdiag C||_F = C_off / ||.|| ;  C = mc mc^T / H ; mc = M - mean_j

@@ -9,70 +9,127 @@
 
 namespace hpmn {
 
+// One work item = one 16-byte quarter (q) of one (b, tp, f) row.  A thread owns U items a grid stride apart and
+// runs them in phases -- U index computations, U id loads, U row loads, U stores -- so U dependent id -> row
+// chains are in flight per thread (Little: ~5 MB of 64-byte requests must be outstanding to cover HBM latency).
+// IdxT = uint32_t whenever the item count fits (32-bit div/mod instead of the 64-bit software routine).
+template <int U, typename IdxT>
 __global__ void __launch_bounds__(256)
 gather_fwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ table, float4* __restrict__ x,
-                  int64_t total, int T, int Tpad, int F, int E4, int front_pad, int mask_id0, int64_t V,
+                  int64_t total_, int T, int Tpad, int F, int E4, int front_pad, int mask_id0, int64_t V,
                   float* __restrict__ iderr) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll 4
-  for (; i < total; i += stride) {
-    int q = (int)(i % E4);
-    int64_t r = i / E4;
-    int f = (int)(r % F); r /= F;
-    int tp = (int)(r % Tpad);
-    int64_t b = r / Tpad;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tp >= front_pad) {
-      int32_t id = __ldg(ids + (b * T + (tp - front_pad)) * F + f);
-      if (id < 0 || (int64_t)id >= V) {
-        if (q == 0) *iderr = 1.0f;          // reported as HPMN_EINVAL by the *_host entry points
-      } else if (!(mask_id0 && id == 0)) {
-        v = ldg_nc_f4(table + (int64_t)id * E4 + q);
+  const IdxT total = (IdxT)total_;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+  for (IdxT i0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    IdxT src[U];
+    int q[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const IdxT i = i0 + (IdxT)u * stride;
+      live[u] = false; src[u] = 0; q[u] = 0;
+      if (i < total && i >= i0) {                   // i >= i0: no wrap-around of the 32-bit index
+        q[u] = (int)(i % (IdxT)E4);
+        IdxT r = i / (IdxT)E4;
+        const IdxT f = r % (IdxT)F; r /= (IdxT)F;
+        const IdxT tp = r % (IdxT)Tpad;
+        const IdxT b = r / (IdxT)Tpad;
+        if (tp >= (IdxT)front_pad) { live[u] = true; src[u] = (b * (IdxT)T + (tp - (IdxT)front_pad)) * (IdxT)F + f; }
       }
     }
-    x[i] = v;
+    int32_t id[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) id[u] = live[u] ? __ldg(ids + src[u]) : 0;
+    float4 v[U];
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool oob = id[u] < 0 || (int64_t)id[u] >= V;
+      bad |= live[u] && oob;
+      if (live[u] && !oob && !(mask_id0 && id[u] == 0)) v[u] = ldg_nc_f4(table + (int64_t)id[u] * E4 + q[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const IdxT i = i0 + (IdxT)u * stride;
+      if (i < total && i >= i0) x[i] = v[u];
+    }
+    if (bad) *iderr = 1.0f;                          // reported as HPMN_EINVAL by the *_host entry points
   }
 }
 
+template <int U, typename IdxT>
 __global__ void __launch_bounds__(256)
 gather_bwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ dx, const float4* __restrict__ dlast,
-                  float* __restrict__ dtable, int64_t total, int T, int Tpad, int F, int E4, int front_pad,
+                  float* __restrict__ dtable, int64_t total_, int T, int Tpad, int F, int E4, int front_pad,
                   int last_tp, int mask_id0, int64_t V) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll 4
-  for (; i < total; i += stride) {
-    int q = (int)(i % E4);
-    int64_t r = i / E4;
-    int f = (int)(r % F); r /= F;
-    int t = (int)(r % T);
-    int64_t b = r / T;
-    int32_t id = __ldg(ids + (b * T + t) * F + f);
-    if (id < 0 || (int64_t)id >= V || (mask_id0 && id == 0)) continue;
-    int tp = t + front_pad;
-    float4 v = ldg_nc_f4(dx + ((b * Tpad + tp) * F + f) * E4 + q);
-    if (dlast != nullptr && tp == last_tp) {
-      float4 w = __ldg(dlast + (b * F + f) * E4 + q);
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  const IdxT total = (IdxT)total_;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+  for (IdxT i0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    IdxT isrc[U], src[U], lsrc[U];
+    int q[U];
+    bool live[U], has_last[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const IdxT i = i0 + (IdxT)u * stride;
+      live[u] = i < total && i >= i0; has_last[u] = false;
+      isrc[u] = 0; src[u] = 0; lsrc[u] = 0; q[u] = 0;
+      if (live[u]) {
+        q[u] = (int)(i % (IdxT)E4);
+        IdxT r = i / (IdxT)E4;
+        const IdxT f = r % (IdxT)F; r /= (IdxT)F;
+        const IdxT t = r % (IdxT)T;
+        const IdxT b = r / (IdxT)T;
+        const IdxT tp = t + (IdxT)front_pad;
+        isrc[u] = (b * (IdxT)T + t) * (IdxT)F + f;
+        src[u] = ((b * (IdxT)Tpad + tp) * (IdxT)F + f) * (IdxT)E4 + (IdxT)q[u];   // < B*Tpad*F*E4, checked by the launcher
+        has_last[u] = dlast != nullptr && tp == (IdxT)last_tp;
+        lsrc[u] = (b * (IdxT)F + f) * (IdxT)E4 + (IdxT)q[u];
+      }
     }
-    red_add_f4(dtable + ((int64_t)id * E4 + q) * 4, v);
+    int32_t id[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      id[u] = live[u] ? __ldg(ids + isrc[u]) : -1;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[u]) v[u] = ldg_nc_f4(dx + src[u]);    // streaming and independent of the id
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (id[u] < 0 || (int64_t)id[u] >= V || (mask_id0 && id[u] == 0)) continue;
+      if (has_last[u]) {
+        const float4 w = __ldg(dlast + lsrc[u]);
+        v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
+      }
+      red_add_f4(dtable + ((int64_t)id[u] * E4 + q[u]) * 4, v[u]);
+    }
   }
 }
 
+// all blocks resident at once (per_sm per SM), every thread running the same number of full U-batches
 static inline int grid_for(int64_t total, int threads, int sms, int per_sm) {
   int64_t need = (total + threads - 1) / threads;
-  int64_t cap = (int64_t)sms * per_sm;
-  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+  if (need < 1) need = 1;
+  const int64_t cap = (int64_t)sms * per_sm;
+  const int64_t iters = (need + cap - 1) / cap;
+  return (int)((need + iters - 1) / iters);
 }
 
 void launch_gather_fwd(const Launch& L, const Dims& d, bool mask_id0, int front_pad, int64_t V, const int32_t* ids,
                        const float* table, float* x, float* iderr, cudaStream_t st) {
   int E4 = d.E / 4;
   int64_t total = (int64_t)d.B * d.Tpad * d.F * E4;
-  int grid = grid_for(total, 256 * 4, L.sms, 8);
-  gather_fwd_kernel<<<grid, 256, 0, st>>>(ids, (const float4*)table, (float4*)x, total, d.T, d.Tpad, d.F, E4,
-                                          front_pad, mask_id0 ? 1 : 0, V, iderr);
+  static int per_sm = 0;     // resident 256-thread blocks per SM (register-limited), queried once
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_fwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 4;
+  int grid = grid_for(total, 256 * 4, L.sms, per_sm);
+  if (total < (int64_t)1 << 31)
+    gather_fwd_kernel<4, uint32_t><<<grid, 256, 0, st>>>(ids, (const float4*)table, (float4*)x, total, d.T, d.Tpad, d.F, E4,
+                                                         front_pad, mask_id0 ? 1 : 0, V, iderr);
+  else
+    gather_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(ids, (const float4*)table, (float4*)x, total, d.T, d.Tpad, d.F, E4,
+                                                        front_pad, mask_id0 ? 1 : 0, V, iderr);
   ++*L.counter;
 }
 
@@ -80,9 +137,16 @@ void launch_gather_bwd(const Launch& L, const Dims& d, bool mask_id0, int front_
                        const int32_t* ids, const float* dx, const float* dlast, float* dtable, cudaStream_t st) {
   int E4 = d.E / 4;
   int64_t total = (int64_t)d.B * d.T * d.F * E4;
-  int grid = grid_for(total, 256 * 4, L.sms, 8);
-  gather_bwd_kernel<<<grid, 256, 0, st>>>(ids, (const float4*)dx, (const float4*)dlast, dtable, total, d.T, d.Tpad,
-                                          d.F, E4, front_pad, d.Tpad - last_offset, mask_id0 ? 1 : 0, V);
+  static int per_sm = 0;
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_bwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 4;
+  int grid = grid_for(total, 256 * 4, L.sms, per_sm);
+  if ((int64_t)d.B * d.Tpad * d.F * E4 < (int64_t)1 << 31)
+    gather_bwd_kernel<4, uint32_t><<<grid, 256, 0, st>>>(ids, (const float4*)dx, (const float4*)dlast, dtable, total, d.T, d.Tpad,
+                                                         d.F, E4, front_pad, d.Tpad - last_offset, mask_id0 ? 1 : 0, V);
+  else
+    gather_bwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(ids, (const float4*)dx, (const float4*)dlast, dtable, total, d.T, d.Tpad,
+                                                        d.F, E4, front_pad, d.Tpad - last_offset, mask_id0 ? 1 : 0, V);
   ++*L.counter;
 }
 

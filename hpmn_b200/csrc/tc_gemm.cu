@@ -67,21 +67,35 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K is consumed in slabs of KS = 32 columns (one 128 x 32 operand buffer per CTA, so 3 CTAs fit an SM for every (K,N)
+// and overlap each other's load / split / MMA / epilogue phases); the accumulator stays in TMEM across the slabs.
+// Epilogue: TMEM -> registers (+bias) -> padded per-warp staging rows in the (now idle) operand buffer -> coalesced
+// 512-byte global stores.  Storing straight from the TMEM register layout (thread = row) costs 32 L2 requests of
+// 16 bytes per instruction and made the projection GEMM request-bound (r1: 2.2 TB/s).
 template <int K, int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, K % 32 == 0 ? 3 : 2)
 tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ bias,
                   float* __restrict__ C, int64_t M) {
-  constexpr int KC = K / 4;                       // 16-byte chunks along K
-  constexpr int CHS_A = 128 * 16 + 16;            // bytes between K-chunks of the A tile (padded)
+  constexpr int KS = K % 32 == 0 ? 32 : K;        // slab width (K = 48: one slab)
+  constexpr int NSLAB = K / KS;
+  static_assert(K % KS == 0 && KS % 8 == 0, "K must be a multiple of the slab width");
+  constexpr int KC = KS / 4;                      // 16-byte chunks along K per slab
+  constexpr int KCB = K / 4;                      // chunks of the whole weight operand
+  constexpr int CHS_A = 128 * 16 + 16;            // bytes between K-chunks of the A slab (padded)
   constexpr int CHS_B = N * 16 + 16;
   constexpr int TCOLS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   constexpr uint32_t IDESC = umma_idesc_tf32(128, N, 0, 0);
+  constexpr int NH = N > 48 ? N / 2 : N;          // columns per epilogue pass
+  constexpr int NPASS = N / NH;
+  constexpr int SROW = NH + 4;                    // staging row stride (floats): an odd number of float4s
+  static_assert(NH % 16 == 0 && ((SROW / 4) & 1) == 1, "epilogue pass width");
+  static_assert(128 * SROW * 4 <= 2 * KC * CHS_A, "staging must fit in the operand buffer");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sAhi = smem_raw;
   unsigned char* sAlo = sAhi + KC * CHS_A;
   unsigned char* sBhi = sAlo + KC * CHS_A;
-  unsigned char* sBlo = sBhi + KC * CHS_B;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sBlo + KC * CHS_B);
+  unsigned char* sBlo = sBhi + KCB * CHS_B;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBlo + KCB * CHS_B);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -102,73 +116,89 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
   const uint32_t tmem = *tslot;
 
   const int64_t tiles = (M + 127) / 128;
-  float4 areg[KC];                                // this thread's 16-byte chunks of the current tile
-  auto load_tile = [&](int64_t tile) {
+  float4 areg[KC];                                // this thread's 16-byte chunks of the current slab
+  auto load_slab = [&](int64_t tile, int s) {
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
       const int e = tid + 128 * i;
       const int row = e / KC, c = e % KC;
       const int64_t m = tile * 128 + row;
-      areg[i] = m < M ? ldg_nc_f4(reinterpret_cast<const float4*>(A + m * lda) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      areg[i] = m < M ? ldg_nc_f4(reinterpret_cast<const float4*>(A + m * lda) + s * KC + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   int64_t tile = blockIdx.x;
-  if (tile < tiles) load_tile(tile);
+  if (tile < tiles) load_slab(tile, 0);
   uint32_t phase = 0;
   for (; tile < tiles; tile += gridDim.x) {
-    // registers -> (hi, lo) -> shared, canonical K-major layout
+#pragma unroll 1
+    for (int s = 0; s < NSLAB; ++s) {
+      // registers -> (hi, lo) -> shared, canonical K-major layout.  The previous user of the buffer (the MMAs of the
+      // previous slab, or the staging reads of the previous tile's epilogue) is complete: see the waits below.
 #pragma unroll
-    for (int i = 0; i < KC; ++i) {
-      const int e = tid + 128 * i;
-      const int row = e / KC, c = e % KC;
-      const float4 v = areg[i];
-      float4 hi, lo;
-      hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-      lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
-      *reinterpret_cast<float4*>(sAhi + c * CHS_A + row * 16) = hi;
-      *reinterpret_cast<float4*>(sAlo + c * CHS_A + row * 16) = lo;
-    }
-    fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t ah = smem_u32(sAhi), al = smem_u32(sAlo), bh = smem_u32(sBhi), bl = smem_u32(sBlo);
-#pragma unroll
-      for (int s = 0; s < K / 8; ++s) {
-        const uint64_t dah = umma_desc(ah + s * 2 * CHS_A, CHS_A, 128), dal = umma_desc(al + s * 2 * CHS_A, CHS_A, 128);
-        const uint64_t dbh = umma_desc(bh + s * 2 * CHS_B, CHS_B, 128), dbl = umma_desc(bl + s * 2 * CHS_B, CHS_B, 128);
-        tc_mma_tf32(tmem, dah, dbh, IDESC, s > 0);
-        tc_mma_tf32(tmem, dal, dbh, IDESC, 1);
-        tc_mma_tf32(tmem, dah, dbl, IDESC, 1);
+      for (int i = 0; i < KC; ++i) {
+        const int e = tid + 128 * i;
+        const int row = e / KC, c = e % KC;
+        const float4 v = areg[i];
+        float4 hi, lo;
+        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+        lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+        *reinterpret_cast<float4*>(sAhi + c * CHS_A + row * 16) = hi;
+        *reinterpret_cast<float4*>(sAlo + c * CHS_A + row * 16) = lo;
       }
-      tc_commit(bar);                             // arrives when every MMA above has finished reading smem / writing TMEM
-    }
-    const int64_t next = tile + gridDim.x;
-    if (next < tiles) load_tile(next);            // next tile's global loads fly during the MMA and the epilogue
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // epilogue: TMEM lane = row, 16 columns per load
-    const int64_t m = tile * 128 + warp * 32 + lane;
+      fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t ah = smem_u32(sAhi), al = smem_u32(sAlo);
+        const uint32_t bh = smem_u32(sBhi) + s * KC * CHS_B, bl = smem_u32(sBlo) + s * KC * CHS_B;
 #pragma unroll
-    for (int cb = 0; cb < N / 16; ++cb) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb * 16, v);
-      if (m < M) {
-        float4* dst = reinterpret_cast<float4*>(C + m * N + cb * 16);
+        for (int q = 0; q < KS / 8; ++q) {
+          const uint64_t dah = umma_desc(ah + q * 2 * CHS_A, CHS_A, 128), dal = umma_desc(al + q * 2 * CHS_A, CHS_A, 128);
+          const uint64_t dbh = umma_desc(bh + q * 2 * CHS_B, CHS_B, 128), dbl = umma_desc(bl + q * 2 * CHS_B, CHS_B, 128);
+          tc_mma_tf32(tmem, dah, dbh, IDESC, (s | q) != 0);
+          tc_mma_tf32(tmem, dal, dbh, IDESC, 1);
+          tc_mma_tf32(tmem, dah, dbl, IDESC, 1);
+        }
+        tc_commit(bar);                           // arrives when every MMA above has finished reading smem / writing TMEM
+      }
+      // the next slab's global loads fly during the MMA (and, after the last slab, the epilogue)
+      if (s + 1 < NSLAB) load_slab(tile, s + 1);
+      else if (tile + gridDim.x < tiles) load_slab(tile + gridDim.x, 0);
+      mbar_wait(bar, phase);                      // every thread: the operand buffer is free, TMEM holds slabs 0..s
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // epilogue: TMEM lane = row.  Each warp stages its own 32 rows (padded) and writes them back coalesced.
+    float* stage = reinterpret_cast<float*>(smem_raw) + warp * 32 * SROW;
+    const int64_t m0 = tile * 128 + warp * 32;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+      for (int cb = 0; cb < NH / 16; ++cb) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + pass * NH + cb * 16, v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           if (bias != nullptr) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + cb * 16) + q);
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + pass * NH + cb * 16) + q);
             o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
           }
-          dst[q] = o;
+          *reinterpret_cast<float4*>(stage + lane * SROW + cb * 16 + q * 4) = o;
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < NH / 4; ++it) {       // 32 rows x NH/4 float4s, 32 consecutive float4s per instruction
+        const int e = it * 32 + lane;
+        const int row = e / (NH / 4), c = e % (NH / 4);
+        const float4 o = *reinterpret_cast<const float4*>(stage + row * SROW + c * 4);
+        if (m0 + row < M) *reinterpret_cast<float4*>(C + (m0 + row) * N + pass * NH + c * 4) = o;
+      }
+      __syncwarp();                               // staging rows free for the next pass
     }
     tc_fence_before();
-    __syncthreads();                              // TMEM drained and smem free before the next tile's writes / MMAs
+    __syncthreads();                              // TMEM drained and staging reads done before the next tile's writes / MMAs
   }
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
@@ -217,7 +247,7 @@ struct WgradProb {
   int64_t ldx, M, rows_per_cta;
   int S, Din, cta_begin, pad_;
 };
-struct WgradBatch { int n, H; WgradProb p[HPMN_MAX_LAYERS]; };
+struct WgradBatch { int n, H, producer_fence, pad_; WgradProb p[HPMN_MAX_LAYERS]; };
 
 template <int DINP>
 __global__ void __launch_bounds__(32 * (WPW + 1))
@@ -323,7 +353,10 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
         const int u = warp + WPW * i, c = 2 * (u >> 1) + lc, k = 16 * (u & 1) + lk;
         put_t(B_hi, B_lo, WCHS_B, 4 * c, k, R.d[i]);
       }
-      fence_proxy_async();
+      // The generic -> async proxy fence sits on the consumer side of the (release) arrive / (acquire) wait pair: here it
+      // compiles to MEMBAR.ALL.CTA, which would also wait for this thread's prefetched global loads of the NEXT three
+      // stages -- every stage would then cost one full DRAM latency (r1: 1.3 us per stage, 2.8 TB/s).
+      if (batch.producer_fence) fence_proxy_async();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
     };
     // four register buffers: ~80 KB of global loads in flight per SM (6.5 TB/s x ~1.5 us needs ~66 KB per SM)
@@ -376,6 +409,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
       for (int sidx = 0; sidx < nst; ++sidx) {
         const int slot = sidx % WNS;
         mbar_wait(&full[slot], (uint32_t)(sidx / WNS) & 1u);
+        fence_proxy_async();                  // producers' generic-proxy stores (ordered by the barrier) -> async proxy
         tc_fence_after();
         const uint32_t base = smem_u32(smem_raw + slot * W_STAGE);
         const uint32_t ah = base, al = base + W_AT, bh = base + 2 * W_AT, bl = base + 2 * W_AT + W_B;
@@ -397,6 +431,9 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   if (warp == WPW) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
+// HPMN_WGRAD_FENCE=1: producers execute the proxy fence themselves (the r1 v1-v6 behaviour)
+static int wgrad_producer_fence() { static int v = -1; if (v < 0) { const char* e = getenv("HPMN_WGRAD_FENCE"); v = (e && e[0] == '1') ? 1 : 0; } return v; }
+
 static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin, int64_t ldx, const float* st, const float* da,
                             float* dWg, float* dbg, float* dWc, float* dbc, int64_t M, int S, int Din, int64_t total_rows) {
   WgradProb& P = b.p[b.n++];
@@ -417,6 +454,7 @@ bool launch_tc_wgrad_all(const Launch& L, const Dims& d, const float* const* xin
   for (int k = 0; k < d.L; ++k)
     if (d.DinP[k] != 32 && d.DinP[k] != 48) return false;
   WgradBatch b32, b48; b32.n = b48.n = 0; b32.H = b48.H = d.H;
+  b32.producer_fence = b48.producer_fence = wgrad_producer_fence();
   int c32 = 0, c48 = 0;
   int64_t rows32 = 0, rows48 = 0;
   for (int k = 0; k < d.L; ++k) (d.DinP[k] == 32 ? rows32 : rows48) += (int64_t)d.B * d.S[k];
@@ -443,7 +481,7 @@ bool launch_tc_wgrad(const Launch& L, const Dims& d, int k, const float* xin, in
                      float* dWg, float* dbg, float* dWc, float* dbc, cudaStream_t st_) {
   const int DinP = d.DinP[k];
   if (DinP != 32 && DinP != 48) return false;
-  WgradBatch b; b.n = 0; b.H = d.H;
+  WgradBatch b; b.n = 0; b.H = d.H; b.producer_fence = wgrad_producer_fence();
   int ctas = 0;
   const int64_t M = (int64_t)d.B * d.S[k];
   wgrad_queue_add(b, ctas, L.sms, xin, ldx, st, da, dWg, dbg, dWc, dbc, M, d.S[k], d.Din[k], M);
@@ -460,16 +498,19 @@ bool launch_tc_wgrad(const Launch& L, const Dims& d, int k, const float* xin, in
 template <int K, int N>
 static void launch_one(const Launch& L, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
                        cudaStream_t st) {
-  constexpr int KC = K / 4;
-  const size_t smem = (size_t)2 * KC * (128 * 16 + 16) + (size_t)2 * KC * (N * 16 + 16) + 64;
+  constexpr int KC = (K % 32 == 0 ? 32 : K) / 4, KCB = K / 4;   // one A slab, the whole weight operand
+  const size_t smem = (size_t)2 * KC * (128 * 16 + 16) + (size_t)2 * KCB * (N * 16 + 16) + 64;
   auto kern = tc_gemm_nn_kernel<K, N>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t tiles = (M + 127) / 128;
   int per_sm = (int)((227 * 1024) / (smem + 1024));   // resident CTAs: shared memory, then the 512-column TMEM budget
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
-  const int grid = (int)(tiles < (int64_t)L.sms * per_sm ? tiles : (int64_t)L.sms * per_sm);
-  kern<<<grid, 128, smem, st>>>(A, lda, W, bias, C, M);
+  // grid = resident CTAs (a multiple of the SM count): tiles are dealt round-robin, so every SM ends within one tile of
+  // the others even though CTAs differ by one tile
+  const int64_t cap = (int64_t)L.sms * per_sm;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  kern<<<grid > 0 ? grid : 1, 128, smem, st>>>(A, lda, W, bias, C, M);
   ++*L.counter;
 }
 
