@@ -212,14 +212,18 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
   return *reinterpret_cast<float2*>(&rd);
 }
-// exp via ex2.approx (<= 2 ulp) -- error ~1e-7 relative, far inside the 1e-4 parity budget
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// exp via ex2.approx (<= 2 ulp) -- error ~1e-7 relative, far inside the 1e-4 parity budget.  The .ftz forms are used
+// directly: __expf() wraps ex2 in a denormal-range fix-up (FSETP + two predicated FMULs) that sits on the dependent chain
+// of every recurrent step, and a flushed denormal changes neither 1/(1+e) nor 1-2/(1+e).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float tanh_f(float x) {
   // |x| >= 0.15: 1 - 2/(1+e^{2x}) (saturates cleanly: e^{2x} -> inf gives 1, -> 0 gives -1).
   // |x| <  0.15: odd Taylor series to x^7 (next term < 1e-9 relative) -- the closed form cancels there and
   // would carry ~1e-7 ABSOLUTE error into values of size 1e-3, i.e. 1e-4 relative.
-  const float e = __expf(2.0f * x);
-  const float big = 1.0f - __fdividef(2.0f, 1.0f + e);
+  const float e = ex2_ftz(x * 2.8853900817779268f);
+  const float big = fmaf(-2.0f, rcp_ftz(1.0f + e), 1.0f);
   const float x2 = x * x;
   const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -17.0f / 315.0f, 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
   return fabsf(x) < 0.15f ? small : big;

@@ -50,11 +50,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// 3xTF32 operand split x = hi + lo.  cvt.rna.tf32.f32 has no native SASS on sm_100a -- it expands to a ~12-instruction
+// LOP3/FSETP/SEL sequence, which made the operand producers of every kernel here issue-bound (r1: 416 instructions per
+// 32-row stage and warp).  Integer form of the same rounding (nearest, ties away from zero: add half a tf32 ulp to the
+// magnitude, clear the 13 low mantissa bits): 2 integer ops for hi, 1 exact FADD + 1 mask for lo (lo is truncated, its
+// error is 2^-10 of a term that is already 2^-11 of x).
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
 // shared-memory matrix descriptor, no swizzle (layout_type 0), sm_100 version bit set
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
@@ -105,7 +107,7 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
   for (int e = tid; e < K * N; e += 128) {
     const int k = e / N, n = e % N;
     const float w = __ldg(W + e);
-    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    const float hi = tf32_rna(w), lo = tf32_lo(w, hi);
     const int off = (k >> 2) * CHS_B + n * 16 + (k & 3) * 4;
     *reinterpret_cast<float*>(sBhi + off) = hi;
     *reinterpret_cast<float*>(sBlo + off) = lo;
@@ -141,7 +143,7 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
         const float4 v = areg[i];
         float4 hi, lo;
         hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-        lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+        lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
         *reinterpret_cast<float4*>(sAhi + c * CHS_A + row * 16) = hi;
         *reinterpret_cast<float4*>(sAlo + c * CHS_A + row * 16) = lo;
       }
@@ -232,10 +234,10 @@ __device__ __forceinline__ void put_t(unsigned char* hi_base, unsigned char* lo_
   *reinterpret_cast<float*>(hi_base + off + 16) = hy;
   *reinterpret_cast<float*>(hi_base + off + 32) = hz;
   *reinterpret_cast<float*>(hi_base + off + 48) = hw;
-  *reinterpret_cast<float*>(lo_base + off) = tf32_rna(v.x - hx);
-  *reinterpret_cast<float*>(lo_base + off + 16) = tf32_rna(v.y - hy);
-  *reinterpret_cast<float*>(lo_base + off + 32) = tf32_rna(v.z - hz);
-  *reinterpret_cast<float*>(lo_base + off + 48) = tf32_rna(v.w - hw);
+  *reinterpret_cast<float*>(lo_base + off) = tf32_lo(v.x, hx);
+  *reinterpret_cast<float*>(lo_base + off + 16) = tf32_lo(v.y, hy);
+  *reinterpret_cast<float*>(lo_base + off + 32) = tf32_lo(v.z, hz);
+  *reinterpret_cast<float*>(lo_base + off + 48) = tf32_lo(v.w, hw);
 }
 
 constexpr int WPW = 8;                 // producer warps (2 per SM sub-partition: the convert/transposing stores are issue-bound)
@@ -303,30 +305,39 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
     // work unit u = warp + 4*i covers 16 rows x 2 adjacent 16-byte chunks: every 32-byte sector a warp touches is
     // used completely (no reliance on L1 hits), and the 32 scalar stores of put_t land in 32 different banks
     const int lk = lane >> 1, lc = lane & 1;
-    auto load = [&](Regs& R, int sidx) {
-      const int64_t m0 = mbeg + (int64_t)sidx * WK;
-      const bool live = sidx < nst;
+    // Every unit of a thread sits on the same row of a stage (WPW is even): one running row counter, one validity test and
+    // one running pointer per unit, bumped by a stage per load() call (the calls walk the stages in order).
+    static_assert(WPW % 2 == 0, "units of a thread must share their row");
+    const int nrows = (int)(mend > mbeg ? mend - mbeg : 0);
+    int rrow = 16 * (warp & 1) + lk;                         // row inside this CTA's range of the next load
+    int hrem = (int)((mbeg + rrow) % S);                     // step index inside the sample: 0 = no predecessor row (zero state)
+    const float4* px[NX]; const float4* pd[3];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { const int u = warp + WPW * i; px[i] = reinterpret_cast<const float4*>(xin + (mbeg + rrow) * ldx) + 2 * (u >> 1) + lc; }
+    const float4* ph = reinterpret_cast<const float4*>(st + (mbeg + rrow) * ST) + 2 * (warp >> 1) + lc;   // row m; h_prev is one row up
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int u = warp + WPW * i; pd[i] = reinterpret_cast<const float4*>(da + (mbeg + rrow) * G3) + 2 * (u >> 1) + lc; }
+    const int64_t sx = (int64_t)WK * ldx / 4;                // float4 strides of one stage
+    auto load = [&](Regs& R, int) {
+      const bool ok = rrow < nrows;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
-        const int64_t m = m0 + 16 * (u & 1) + lk;
-        R.x[i] = (live && u < NXU && m < mend) ? __ldg(reinterpret_cast<const float4*>(xin + m * ldx) + c) : z;
+        const int u = warp + WPW * i;
+        R.x[i] = (ok && u < NXU) ? __ldg(px[i]) : z;
+        px[i] += sx;
       }
-#pragma unroll
-      for (int i = 0; i < 1; ++i) {
-        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
-        const int64_t m = m0 + 16 * (u & 1) + lk;
-        const bool ok = live && m < mend;
-        R.h[i] = (ok && m % S != 0) ? __ldg(reinterpret_cast<const float4*>(st + (m - 1) * ST) + c) : z;
-        R.r[i] = ok ? __ldg(reinterpret_cast<const float4*>(st + m * ST + HP) + c) : z;
-      }
+      R.h[0] = (ok && hrem != 0) ? __ldg(ph - ST / 4) : z;
+      R.r[0] = ok ? __ldg(ph + HP / 4) : z;
+      ph += WK * ST / 4;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
-        const int64_t m = m0 + 16 * (u & 1) + lk;
-        R.d[i] = (live && m < mend) ? __ldg(reinterpret_cast<const float4*>(da + m * G3) + c) : z;
+        R.d[i] = ok ? __ldg(pd[i]) : z;
+        pd[i] += WK * G3 / 4;
       }
+      rrow += WK;
+      hrem += WK;
+      while (hrem >= S) hrem -= S;
     };
     auto store = [&](const Regs& R, int sidx) {
       const int slot = sidx % WNS;

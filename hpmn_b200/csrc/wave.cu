@@ -57,6 +57,22 @@ __device__ __forceinline__ float dotn(const float* v, const float2 (&w)[16], flo
   return (a0.x + a1.x) + (a0.y + a1.y);
 }
 
+// same dot product as four chains of four FFMA2 (+ one more add level): for the dot products that sit alone on the
+// dependent chain of a step (the candidate mat-vec, the first adjoint mat-vec) the chain latency is what counts
+__device__ __forceinline__ float dotn4(const float* v, const float2 (&w)[16], float init) {
+  float2 a0 = make_float2(init, 0.f), a1 = make_float2(0.f, 0.f), a2 = a1, a3 = a1;
+  const float4* s4 = reinterpret_cast<const float4*>(v);
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    const float4 x = s4[q], y = s4[q + 1];
+    a0 = ffma2(make_float2(x.x, x.y), w[2 * q], a0);
+    a1 = ffma2(make_float2(x.z, x.w), w[2 * q + 1], a1);
+    a2 = ffma2(make_float2(y.x, y.y), w[2 * q + 2], a2);
+    a3 = ffma2(make_float2(y.z, y.w), w[2 * q + 3], a3);
+  }
+  return ((a0.x + a1.x) + (a2.x + a3.x)) + ((a0.y + a1.y) + (a2.y + a3.y));
+}
+
 struct Handoff3 {                  // projected input (fwd) / da row (bwd) of layer 1: 96 floats per slot
   float ring[HRS][G3];
   uint64_t full[HRS], empty[HRS];
@@ -233,7 +249,7 @@ __device__ __forceinline__ float wave_layer(const WaveArgs& a, int k, int b, int
     const float u = sigmoid_f(dotn(hprev, wu, au));
     sh_rh[j] = r * h;                                    // util.py:98
     __syncwarp();
-    const float c = tanh_f(dotn(sh_rh, wc, ac));         // util.py:107
+    const float c = tanh_f(dotn4(sh_rh, wc, ac));        // util.py:107
     h = fmaf(u, h - c, c);                               // util.py:109
     orow[j] = h; orow[HP + j] = r; orow[2 * HP + j] = u; orow[3 * HP + j] = c;
     hprev = orow;
@@ -466,9 +482,12 @@ struct WaveBwdSmem {
   }
 };
 
-template <int CH, int NS>
+template <int CH, int NS, bool DBG>
 __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int b, int i, unsigned char* reg, Handoff* hin,
                                                Handoff* hout, const float2* myWxT) {
+  long long w_in = 0, w_out = 0, w_tma = 0;               // DBG: cycles blocked on hand-off in / out and on the TMA ring
+  const bool dbg = DBG && blockIdx.x == 0;
+  const long long t_start = DBG ? clock64() : 0;
   const int S = a.S[k], H = a.H, L = a.L;
   const int period = k < L - 1 ? a.P[k] : 1;             // firing period towards layer k+1
   float* s_st = reinterpret_cast<float*>(reg);           // [NS][(CH+1)*ST]
@@ -519,7 +538,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
     if (hin != nullptr && --to_fire == 0) {              // this step fed layer k+1 in the forward pass
       to_fire = period;
       const int slot = got & (HRS - 1);
-      mbar_wait(&hin->full[slot], (got / HRS) & 1u);
+      mbar_wait_t(&hin->full[slot], (got / HRS) & 1u, w_in, dbg);
       dh += hin->ring[slot][i];
       ++got;
       __syncwarp();
@@ -531,7 +550,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
     const float dac = dc * (1.f - c * c);
     sh_c[i] = dac;
     __syncwarp();
-    const float drh = dotn(sh_c, wcT, 0.f);              // (da_c * Wc^T)[Din + i]
+    const float drh = dotn4(sh_c, wcT, 0.f);             // (da_c * Wc^T)[Din + i]
     const float dr = drh * hp;
     dhp = fmaf(drh, r, dhp);
     const float dar = dr * r * (1.f - r);
@@ -561,7 +580,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
       }
       const float dx = (x0.x + x0.y) + (x1.x + x1.y) + (x2.x + x2.y);
       const int slot = sent & (HRS - 1);
-      if (sent >= HRS) mbar_wait(&hout->empty[slot], (sent / HRS - 1) & 1u);
+      if (sent >= HRS) mbar_wait_t(&hout->empty[slot], (sent / HRS - 1) & 1u, w_out, dbg);
       hout->ring[slot][i] = dx;
       ++sent;
       __syncwarp();
@@ -575,7 +594,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
     const int stage = it % NS;
     const int s0 = ci * CH;
     const int len = min(CH, S - s0);
-    mbar_wait(&full[stage], (uint32_t)(it / NS) & 1u);
+    mbar_wait_t(&full[stage], (uint32_t)(it / NS) & 1u, w_tma, dbg);
     float* ob = s_da + (it & 1) * CH * G3;
     if (it >= 2) {
       if (i == 0) bulk_wait_read<1>();
@@ -598,9 +617,13 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
   }
   if (i == 0) bulk_wait_read<0>();
   __syncwarp();
+  if (dbg && i == 0 && b == 0)
+    printf("wave_bwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld\n", k, S,
+           clock64() - t_start, (clock64() - t_start) / S, w_in, w_out, w_tma);
 }
 
 // Registers are partitioned per SM sub-partition (16 K each): 10 warps = 3 on one SMSP = at most 168 per thread.
+template <bool DBG>
 __global__ void __launch_bounds__(320)
 wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
@@ -631,9 +654,9 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
   Handoff* hin = k < L - 1 ? &hand[k * nspc + si] : nullptr;        // from layer k+1
   Handoff* hout = k > 0 ? &hand[(k - 1) * nspc + si] : nullptr;     // to layer k-1
   if (k == 0) {
-    wave_bwd_layer<BCH0, BNS0>(a, k, b, i, dsm + sm.l0 + si * bwd_region_bytes(BCH0, BNS0), hin, nullptr, nullptr);
+    wave_bwd_layer<BCH0, BNS0, DBG>(a, k, b, i, dsm + sm.l0 + si * bwd_region_bytes(BCH0, BNS0), hin, nullptr, nullptr);
   } else {
-    wave_bwd_layer<BCHK, BNSK>(a, k, b, i, dsm + sm.lk + ((k - 1) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
+    wave_bwd_layer<BCHK, BNSK, DBG>(a, k, b, i, dsm + sm.lk + ((k - 1) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
                                sWxT + (size_t)(k - 1) * 48 * HP);
   }
 }
@@ -648,11 +671,18 @@ bool launch_wave_bwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   a.pw = pw; a.dmemory = dmemory;
   a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
   for (int k = 0; k < d.L; ++k) { a.st[k] = st[k]; a.da[k] = da[k]; a.WhT[k] = pk.WhT[k]; a.WxT[k] = pk.WxT[k]; a.S[k] = d.S[k]; a.P[k] = d.P[k]; }
-  cudaFuncSetAttribute(wave_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
   const int grid = (d.B + nspc - 1) / nspc;
   const WarpPlan wp = plan_warps(d.L, nspc, false);
   for (int i = 0; i < 16; ++i) { a.wlayer[i] = wp.layer[i]; a.wsample[i] = wp.sample[i]; a.whelper[i] = wp.helper[i]; }
-  wave_bwd_kernel<<<grid, 32 * wp.n, sm.total, st_>>>(a);
+  bool debug = false;
+  { static int once = 0; const char* e = getenv("HPMN_WAVE_DEBUG"); debug = e && e[0] == '1' && once++ == 3; }   // 4th call only
+  if (debug) {
+    cudaFuncSetAttribute(wave_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    wave_bwd_kernel<true><<<grid, 32 * wp.n, sm.total, st_>>>(a);
+  } else {
+    cudaFuncSetAttribute(wave_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    wave_bwd_kernel<false><<<grid, 32 * wp.n, sm.total, st_>>>(a);
+  }
   { cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_bwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * d.L * nspc, sm.total); return false; } }
   ++*L.counter;
