@@ -219,7 +219,10 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
 // scattered into the TF weight layout once at the end.
 // ---------------------------------------------------------------------------------------------------
 constexpr int WK = 32;                 // rows per stage (= MMA K per stage)
-constexpr int WNS = 3;                 // stages
+#ifndef HPMN_WNS
+#define HPMN_WNS 3
+#endif
+constexpr int WNS = HPMN_WNS;          // stages
 constexpr int WCHS_A = 128 * 16 + 16;  // bytes between 4-row K chunks of the feature tile (padded)
 constexpr int WCHS_B = 96 * 16 + 16;
 constexpr int W_AT = (WK / 4) * WCHS_A;

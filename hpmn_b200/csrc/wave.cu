@@ -258,10 +258,19 @@ __device__ __forceinline__ float gru_fwd_step(const FwdW& w, float ar, float au,
 // TMA_IN (layer 0): projected inputs stream in from global memory, chunks of 16 steps.  Otherwise (layer 1): the helper
 // warp delivers chunks of 8 pre-scaled projected rows through `inr` -- layer 1 runs the same loop as layer 0 at half its
 // rate, so it never holds layer 0 back.
+// Layer 0's chunk I/O as seen by the helper warp that serves it (wave_proj_helper): ncu / the cycle counters put the lane-0
+// bulk store + TMA refill + bulk_wait_read at 29 k of layer 0's 568 k cycles, and the helper has the slack.
+struct L0Io { float* s_in; float* s_out; uint64_t* full; const float* pp; float* so; int S; };
+
 template <bool TMA_IN, bool FIRE2>
 __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b, int j, float* s_in, uint64_t* full,
                                                  InRing* inr, float* s_out, float* sh_rh, float* sh_h, Handoff* hout) {
   constexpr int CH = TMA_IN ? WIN : BLK;
+  // SELF_IO = false (layer 0 with a helper): the helper warp issues this warp's bulk stores and TMA refills.  It learns that
+  // chunk c is complete from the hand-off barrier of the chunk's last block (this warp fences its rows for the async proxy
+  // before that arrive), stores chunk c and requests input chunk c+2; it makes sure the store has read its source before it
+  // releases the NEXT hand-off group, which this warp waits for anyway before it rewrites output buffer c & 1 in chunk c+2.
+  constexpr bool SELF_IO = !(TMA_IN && FIRE2);
   const int S = a.S[k];
   FwdW w;
   load_fwd_weights(w, a.pw + a.Wh[k], j);
@@ -275,7 +284,7 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
     }
     __syncwarp();
     if (j == 0)
-      for (int c = 0; c < WNS0 && c < nch; ++c) {
+      for (int c = 0; c < (SELF_IO ? WNS0 : 2) && c < nch; ++c) {   // served by the helper: chunk c+2 is requested when chunk c is done
         const int len = min(CH, S - c * CH);
         mbar_expect_tx(&full[c], (uint32_t)len * G3 * 4);
         bulk_g2s(s_in + c * CH * G3, pp + (int64_t)c * CH * G3, (uint32_t)len * G3 * 4, &full[c]);
@@ -284,6 +293,7 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
   }
 
   long long w_out = 0, w_tma = 0, w_steps = 0;           // debug: cycles blocked on the helper / on TMA, cycles inside the step blocks
+  long long w_q[4] = {0, 0, 0, 0};                       // debug: bulk_wait_read | gfull arrive | proxy fence | lane-0 bulk store + TMA refill
   const bool dbg = a.debug != 0 && blockIdx.x == 0;
   const long long t_start = clock64();
   float h = 0.f;                                         // zero_state, code/rnn.py:588 (sh_h starts as the zero row)
@@ -305,10 +315,12 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
       mbar_wait_t(&inr->full[stage], (uint32_t)(c >> 1) & 1u, w_tma, dbg);
       ib = &inr->row[stage][0][0];
     }
-    if (c >= 2) {                                        // the bulk store that read this buffer two chunks ago
+    const long long tq0 = dbg ? clock64() : 0;
+    if (SELF_IO && c >= 2) {                             // the bulk store that read this buffer two chunks ago
       if (j == 0) bulk_wait_read<1>();
       __syncwarp();
     }
+    if (dbg) w_q[0] += clock64() - tq0;
     const int nb = len / BLK;
     for (int half = 0; half < nb; ++half) {
       const int blk = c * (CH / BLK) + half, g = blk & 1;
@@ -332,7 +344,10 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
         if (FIRE2) rg += (FUNR / 2) * HP;
       }
       if (dbg) w_steps += clock64() - tb0;
+      const long long tq1 = dbg ? clock64() : 0;
+      if (!SELF_IO && (half + 1) * BLK == len) { fence_proxy_async(); __syncwarp(); }   // last block of the chunk: rows -> async proxy
       if (FIRE2 && j == 0) mbar_arrive(&hout->gfull[g]);
+      if (dbg) { __syncwarp(); w_q[1] += clock64() - tq1; }
     }
     const int t0 = nb * BLK;
     if (t0 < len) {                                      // ragged tail (< 8 steps, last chunk only): same step, runtime offsets
@@ -343,10 +358,15 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
         if (FIRE2 && ((t - t0) & 1)) hout->ring[g * HG + ((t - t0) >> 1)][j] = h;
         __syncwarp();
       }
+      if (!SELF_IO) { fence_proxy_async(); __syncwarp(); }
       if (FIRE2 && len - t0 >= 2 && j == 0) mbar_arrive(&hout->gfull[g]);
     }
+    if (!SELF_IO) continue;                              // the helper stores the chunk and refills the input ring
+    const long long tq2 = dbg ? clock64() : 0;
     fence_proxy_async();                                 // generic-proxy writes of ob -> visible to the bulk store
     __syncwarp();
+    if (dbg) { w_q[2] += clock64() - tq2; }
+    const long long tq3 = dbg ? clock64() : 0;
     if (j == 0) {
       bulk_s2g(so + (int64_t)c * CH * ST, ob, (uint32_t)len * ST * 4);
       bulk_commit();
@@ -361,12 +381,15 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
         mbar_arrive(&inr->empty[stage]);                 // chunk consumed: the helper may refill it
       }
     }
+    if (dbg) { __syncwarp(); w_q[3] += clock64() - tq3; }
   }
-  if (j == 0) bulk_wait_read<0>();
+  if (SELF_IO && j == 0) bulk_wait_read<0>();
   __syncwarp();
   if (dbg && j == 0 && b == 0)
-    printf("wave_fwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld  in-blocks %lld\n", k, S,
-           clock64() - t_start, (clock64() - t_start) / S, TMA_IN ? 0ll : w_tma, w_out, TMA_IN ? w_tma : 0ll, w_steps);
+    printf("wave_fwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld  in-blocks %lld  "
+           "[wait_read %lld  arrive %lld  fence %lld  io %lld]\n", k, S,
+           clock64() - t_start, (clock64() - t_start) / S, TMA_IN ? 0ll : w_tma, w_out, TMA_IN ? w_tma : 0ll, w_steps, w_q[0], w_q[1],
+           w_q[2], w_q[3]);
   return h;
 }
 
@@ -462,7 +485,8 @@ __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, 
 
 // Helper warp of layer 1: applies W_x^(1) (pre-scaled, in registers) to every hand-off of layer 0 and delivers the projected
 // rows to layer 1 in chunks of BLK, so that layer 1 runs layer 0's loop at half its rate.
-__device__ __forceinline__ void wave_proj_helper(int n, int j, const float2* myWx, const float* myBx, Handoff* hin, InRing* inr) {
+__device__ __forceinline__ void wave_proj_helper(int n, int j, const float2* myWx, const float* myBx, Handoff* hin, InRing* inr,
+                                                 const L0Io io) {
   HalfW w[3];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
@@ -471,12 +495,34 @@ __device__ __forceinline__ void wave_proj_helper(int n, int j, const float2* myW
   const float b0 = myBx[j], b1 = myBx[HP + j], b2 = myBx[2 * HP + j];
   for (unsigned idx = 0; idx < (unsigned)n; ++idx) {
     const int slot = idx & (HRS - 1), g = (idx / HG) & 1;
-    if ((idx & (HG - 1)) == 0) mbar_wait(&hin->gfull[g], (idx / HRS) & 1u);
+    if ((idx & (HG - 1)) == 0) {
+      mbar_wait(&hin->gfull[g], (idx / HRS) & 1u);
+      // layer 0's I/O: group `grp` closing a chunk (odd group, or the last one) means its 16 (or fewer) rows are final and fenced
+      const int grp = idx / HG, ngrp = (n + HG - 1) / HG;
+      if (j == 0 && ((grp & 1) || grp == ngrp - 1)) {
+        const int c = grp >> 1, nch = (io.S + WIN - 1) / WIN;
+        const int len = min(WIN, io.S - c * WIN);
+        bulk_s2g(io.so + (int64_t)c * WIN * ST, io.s_out + (c & 1) * WIN * ST, (uint32_t)len * ST * 4);
+        bulk_commit();
+        const int cn = c + 2;
+        if (cn < nch) {
+          const int ln = min(WIN, io.S - cn * WIN), stage = cn % WNS0;
+          mbar_expect_tx(&io.full[stage], (uint32_t)ln * G3 * 4);
+          bulk_g2s(io.s_in + stage * WIN * G3, io.pp + (int64_t)cn * WIN * G3, (uint32_t)ln * G3 * 4, &io.full[stage]);
+        }
+      }
+      __syncwarp();
+    }
     float4 v[4];
     load_vec_half(v, hin->ring[slot], j);
     const Part p0 = half_part(v, w[0], b0), p1 = half_part(v, w[1], b1), p2 = half_part(v, w[2], b2);
     __syncwarp();
-    if (j == 0 && ((idx & (HG - 1)) == HG - 1 || idx + 1 == (unsigned)n)) mbar_arrive(&hin->gempty[g]);   // group free again
+    if (j == 0 && ((idx & (HG - 1)) == HG - 1 || idx + 1 == (unsigned)n)) {
+      // group free again.  Layer 0 rewrites output buffer c & 1 two chunks after chunk c, behind this barrier for the group
+      // that follows the one whose arrival triggered the store of chunk c: by now that store has long read its source
+      bulk_wait_read<0>();
+      mbar_arrive(&hin->gempty[g]);
+    }
     const float ar = half_finish(p0.m, p0.o), au = half_finish(p1.m, p1.o), ac = half_finish(p2.m, p2.o);
     const int stage = (idx / BLK) & 1, rowi = idx & (BLK - 1);
     if (rowi == 0 && idx >= 2 * BLK) mbar_wait(&inr->empty[stage], (idx / (2 * BLK) - 1) & 1u);
@@ -530,7 +576,11 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
   if (b >= a.B || k < 0) return;                         // ragged last CTA: the whole warp leaves together
 
   if (helper) {                                          // layer 1's projection warp
-    wave_proj_helper(a.S[1], j, sWx, sBx, &hand[0 * nspc + si], &inr[si]);
+    float* s_in0 = reinterpret_cast<float*>(dsm + sm.l0 + si * sm.r0);      // layer 0's region, same carve-up as below
+    float* s_out0 = s_in0 + WNS0 * WIN * G3;
+    uint64_t* full0 = reinterpret_cast<uint64_t*>(s_out0 + 2 * WIN * ST + 64);
+    const L0Io io{s_in0, s_out0, full0, a.proj0 + (int64_t)b * a.S[0] * G3, a.st[0] + (int64_t)b * a.S[0] * ST, a.S[0]};
+    wave_proj_helper(a.S[1], j, sWx, sBx, &hand[0 * nspc + si], &inr[si], io);
     return;
   }
   unsigned char* reg = k == 0 ? dsm + sm.l0 + si * sm.r0 : dsm + sm.lk + ((k - 1) * nspc + si) * sm.r1;
@@ -599,7 +649,8 @@ bool launch_wave_fwd(const Launch& L, const Dims& d, const PackLayout& pk, const
 // the weight-gradient kernel and, for layer 0, the dX GEMM that feeds the embedding scatter.
 // =====================================================================================================
 constexpr int BCH0 = 8, BNS0 = 3;   // layers 0 and 1: steps per chunk, state ring stages
-constexpr int BCHK = 4, BNSK = 2;   // layers >= 2 (not on the critical path): smaller rings
+constexpr int BCHK = 4, BNSK = 2;   // layers >= 3 (not on the critical path): smaller rings
+constexpr int BCH2 = 8;             // layer 2: 8-step chunks (its per-chunk I/O was 150 of its ~2000 cycles per step)
 
 struct WaveBwdArgs {
   const float* pw;
@@ -617,7 +668,7 @@ __host__ __device__ constexpr int bwd_region_bytes(int ch, int ns) {
 }
 
 struct WaveBwdSmem {
-  int wxt, hand, hand3, l0, l1, lk, total;
+  int wxt, hand, hand3, l0, l1, l2, lk, total;
   __host__ __device__ WaveBwdSmem(int L, int nspc) {
     int off = 0;
     wxt = off; off += (L - 1) * 3 * 8 * 2 * HP * 8;        // float2 [g][q][mine|other][lane] per layer >= 1
@@ -628,7 +679,8 @@ struct WaveBwdSmem {
     off = (off + 127) & ~127;
     l0 = off; off += nspc * bwd_region_bytes(BCH0, BNS0);
     l1 = off; off += (L > 1 ? nspc : 0) * bwd_region_bytes(BCH0, BNS0);   // layer 1 runs the same loop as layer 0
-    lk = off; off += (L > 2 ? L - 2 : 0) * nspc * bwd_region_bytes(BCHK, BNSK);
+    l2 = off; off += (L > 2 ? nspc : 0) * bwd_region_bytes(BCH2, BNSK);        // layer 2: next in line for the critical path
+    lk = off; off += (L > 3 ? L - 3 : 0) * nspc * bwd_region_bytes(BCHK, BNSK);
     total = off;
   }
 };
@@ -645,11 +697,14 @@ __device__ __forceinline__ void load_bwd_weights(BwdW& w, const float* WhT /*[3]
 // -> dh';  every factor that does not depend on dh (1-u, 1-c^2, (h_prev-c) u (1-u), r (1-r) h_prev) is formed from the saved
 // state before dh arrives, da_u is broadcast together with da_c so that its mat-vec fills the bubbles of the chain.
 // row = this lane's column of buffer row t (h_{s-1}; row t+1 holds r|u|c of step s); orow = of the da row; add = gradient
-// arriving from the layer above for the step BELOW this one (0 if that step did not fire).  vr|vu|vc return this lane's
-// halves of the broadcast da_r|da_u|da_c (for the caller's dx mat-vec).  The caller closes the step with __syncwarp().
+// arriving from the layer above for the step BELOW this one (0 if that step did not fire).  WITH_DX (layers >= 2): the
+// gradient handed down to the layer below, dx = da W_x^T, is accumulated from the same broadcast halves as they arrive
+// (W_x^T from shared memory, [g][q][mine|other][lane]) -- nothing but six accumulators stays live for it.
+// The caller closes the step with __syncwarp().
+template <bool WITH_DX>
 __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, bool first_step, float dh, float add, int i,
                                               float* sh_c, float* sh_r, float* sh_u, float* orow, float& dar, float& dau,
-                                              float& dac, float4 (&vr)[4], float4 (&vu)[4], float4 (&vc)[4]) {
+                                              float& dac, const float2* myWxT, float& dx) {
   const float hp = first_step ? 0.f : row[0];            // zero state before step 0
   const float r = row[ST + HP], u = row[ST + 2 * HP], c = row[ST + 3 * HP];
   const float omu = 1.f - u;
@@ -660,18 +715,27 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
   sh_c[i] = dac;
   sh_u[i] = dau;
   __syncwarp();
-  load_vec_half(vc, sh_c, i);
+  float4 v[4], vu[4];
+  load_vec_half(v, sh_c, i);
   load_vec_half(vu, sh_u, i);
-  const Part pc = half_part(vc, w.c, 0.f);
+  const Part pc = half_part(v, w.c, 0.f);
   const float drh = half_finish(pc.m, pc.o);             // (da_c Wc^T)[Din + i]
   dar = drh * gr;
   sh_r[i] = dar;
   __syncwarp();
-  load_vec_half(vr, sh_r, i);
+  float2 xm0 = make_float2(0.f, 0.f), xo0 = xm0, xm1 = xm0, xo1 = xm0, xm2 = xm0, xo2 = xm0;
+  if (WITH_DX) half_part_smem(v, myWxT + (2 * 8) * 2 * HP + i, 2, xm2, xo2);    // rows 64..95 of W_x^T: da_c
+  load_vec_half(v, sh_r, i);
   const Part pu = half_part(vu, w.u, fmaf(dh, u, add));  // off the chain
-  const Part pr = half_part(vr, w.r, drh * r);
+  if (WITH_DX) half_part_smem(vu, myWxT + (1 * 8) * 2 * HP + i, 2, xm1, xo1);   // rows 32..63: da_u
+  const Part pr = half_part(v, w.r, drh * r);
   orow[0] = dar; orow[HP] = dau; orow[2 * HP] = dac;
-  return half_finish(pr.m + pu.m, pr.o + pu.o);          // gradient wrt h_{s-1} (+ the share of the layer above)
+  const float dhn = half_finish(pr.m + pu.m, pr.o + pu.o);   // gradient wrt h_{s-1} (+ the share of the layer above)
+  if (WITH_DX) {
+    half_part_smem(v, myWxT + (0 * 8) * 2 * HP + i, 2, xm0, xo0);               // rows 0..31: da_r
+    dx = half_finish(((xm0.x + xm0.y) + (xm1.x + xm1.y)) + (xm2.x + xm2.y), ((xo0.x + xo0.y) + (xo1.x + xo1.y)) + (xo2.x + xo2.y));
+  }
+  return dhn;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -679,9 +743,17 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
 // round trip); no branch or address arithmetic inside a chunk.  FIRE2 = false: no layer above.  OUT_DA (layer 1): hand the
 // da row of every step to the dx helper.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool FIRE2, bool OUT_DA, bool DBG>
+// Layer 0's chunk I/O as seen by the dx helper that serves it (see wave_bwd_fast, SERVED)
+struct L0BwdIo { float* s_st; float* s_da; uint64_t* full; const float* sb; float* dab; int S; };
+
+// SERVED (layer 0 with a helper): the dx helper issues this warp's bulk stores and state-ring refills.  It learns that chunk
+// `it` is consumed from the group-empty barrier (this warp fences its da rows for the async proxy before that arrive) and
+// serves it before it produces group it+2 -- so the group-full barrier this warp waits on anyway for chunk it+2 also
+// tells it that da buffer it & 1 is free again and that the state rows of chunk it+3 are on their way.
+template <bool FIRE2, bool OUT_DA, bool SERVED, bool DBG>
 __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b, int i, unsigned char* reg, Handoff* hin,
                                               Handoff3* hda) {
+  static_assert(!SERVED || FIRE2, "only a layer with a layer above has a helper");
   constexpr int CH = BCH0, NS = BNS0;
   static_assert(CH == BLK && CH == 2 * HG, "one chunk = one hand-off group of the layer above");
   long long w_in = 0, w_out = 0, w_tma = 0;               // DBG: cycles blocked on hand-off in / out and on the TMA ring
@@ -721,9 +793,8 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
   float dh = i < H ? __ldg(a.dmemory + ((int64_t)b * L + k) * H + i) : 0.f;   // memory-slot gradient enters at the last step
 
   auto step = [&](const float* row, float* orow, bool first_step, float add) {
-    float dar, dau, dac;
-    float4 vr[4], vu[4], vc[4];
-    dh = gru_bwd_step(w, row, first_step, dh, add, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, vr, vu, vc);
+    float dar, dau, dac, dx_unused;
+    dh = gru_bwd_step<false>(w, row, first_step, dh, add, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, nullptr, dx_unused);
     if (OUT_DA) {                                        // every step of layer 1 fed a firing step of layer 0: da row -> helper
       const int slot = sent & (HRS - 1);
       if (sent >= HRS) mbar_wait_t(&hda->empty[slot], (sent / HRS - 1) & 1u, w_out, dbg);
@@ -743,7 +814,7 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
     const int g = it & 1;
     mbar_wait_t(&full[stage], (uint32_t)(it / NS) & 1u, w_tma, dbg);
     float* ob = s_da + (it & 1) * CH * G3 + i;
-    if (it >= 2) {
+    if (!SERVED && it >= 2) {
       if (i == 0) bulk_wait_read<1>();
       __syncwarp();
     }
@@ -773,6 +844,7 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
       for (int t = len - 1; t >= 0; --t)
         step(ib + t * ST, ob + t * G3, s0 + t == 0, (FIRE2 && t > 0 && ((t - 1) & 1)) ? rg[(HG - 1 - ((t - 1) >> 1)) * HP] : 0.f);
     }
+    if (SERVED) { fence_proxy_async(); __syncwarp(); }   // da rows -> async proxy before the helper is told the chunk is done
     if (FIRE2) {
       if (i == 0) mbar_arrive(&hin->gempty[g]);          // every lane's reads of the group precede the step's last __syncwarp
       if (it + 1 < nch) {                                // step s0-1 (odd) fired: its share is row 0 of the next group
@@ -780,6 +852,7 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
         dh += hin->ring[(g ^ 1) * HG][i];
       }
     }
+    if (SERVED) continue;
     fence_proxy_async();
     __syncwarp();
     if (i == 0) {
@@ -788,7 +861,7 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
       if (it + NS < nch) issue(nch - 1 - (it + NS), stage);
     }
   }
-  if (i == 0) bulk_wait_read<0>();
+  if (!SERVED && i == 0) bulk_wait_read<0>();
   __syncwarp();
   if (dbg && i == 0 && b == 0)
     printf("wave_bwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld\n", k, S,
@@ -797,7 +870,22 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
 
 // Helper warp of layer 1: dx = da W_x^(1)T for every step of layer 1, W_x^T in registers, handed to layer 0 in groups of
 // HG rows aligned with layer 0's chunks.
-__device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, const float2* myWxT, Handoff3* hda, Handoff* hout) {
+__device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, const float2* myWxT, Handoff3* hda, Handoff* hout,
+                                                   const L0BwdIo io) {
+  constexpr int CH = BCH0, NS = BNS0;
+  const int nch0 = (io.S + CH - 1) / CH;
+  auto serve = [&](int it) {                             // lane 0: layer 0 has consumed chunk `it` (reverse order) and fenced its da rows
+    const int s0 = (nch0 - 1 - it) * CH, len = min(CH, io.S - s0);
+    bulk_s2g(io.dab + (int64_t)s0 * G3, io.s_da + (it & 1) * CH * G3, (uint32_t)len * G3 * 4);
+    bulk_commit();
+    if (it + NS < nch0) {                                // refill the state stage the chunk has just released
+      const int ci = nch0 - 1 - (it + NS), stage = it % NS, t0 = ci * CH, ln = min(CH, io.S - t0);
+      const uint32_t rows = (uint32_t)(t0 > 0 ? ln + 1 : ln);
+      mbar_expect_tx(&io.full[stage], rows * ST * 4);
+      if (t0 > 0) bulk_g2s(io.s_st + stage * (CH + 1) * ST, io.sb + (int64_t)(t0 - 1) * ST, rows * ST * 4, &io.full[stage]);
+      else bulk_g2s(io.s_st + stage * (CH + 1) * ST + ST, io.sb, rows * ST * 4, &io.full[stage]);
+    }
+  };
   HalfW w[3];                                            // gate g: rows g*32 .. g*32+31 of W_x^T
 #pragma unroll
   for (int g = 0; g < 3; ++g)
@@ -817,13 +905,25 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
     if (i == 0) mbar_arrive(&hda->empty[slot]);          // row consumed
     const unsigned v = idx + vofs;                       // virtual hand-off index: group = v / HG, ring slot = v % HRS
     const int g = (v / HG) & 1;
-    if ((v & (HG - 1)) == 0 && v >= HRS) mbar_wait(&hout->gempty[g], (v / HRS - 1) & 1u);
+    if ((v & (HG - 1)) == 0 && v >= HRS) {
+      mbar_wait(&hout->gempty[g], (v / HRS - 1) & 1u);   // layer 0 is done with group v/HG - 2 = its chunk of that index
+      if (i == 0) serve((int)(v / HG) - 2);
+      __syncwarp();
+    }
     hout->ring[v & (HRS - 1)][i] = dx;
     if (((v + 1) & (HG - 1)) == 0 || idx + 1 == n) {
       __syncwarp();
-      if (i == 0) mbar_arrive(&hout->gfull[g]);
+      // layer 0 rewrites da buffer it & 1 in chunk it+2, behind this barrier: the store of chunk it (issued when this group
+      // was started) must have read its source by then -- it has, four layer-1 steps later
+      if (i == 0) { bulk_wait_read<0>(); mbar_arrive(&hout->gfull[g]); }
     }
   }
+  for (int G = max(0, nch0 - 2); G < nch0; ++G) {        // the last two chunks of layer 0
+    mbar_wait(&hout->gempty[G & 1], (uint32_t)(G / 2) & 1u);
+    if (i == 0) serve(G);
+    __syncwarp();
+  }
+  if (i == 0) bulk_wait_read<0>();
 }
 
 // Layers >= 2: any period; dx = da W_x^T in-warp with W_x^T from shared memory (K-half layout), per-slot hand-off below,
@@ -881,15 +981,9 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
       __syncwarp();
       if (i == 0) mbar_arrive(&hin->empty[slot]);
     }
-    float dar, dau, dac;
-    float4 vr[4], vu[4], vc[4];
-    dh = gru_bwd_step(w, row, first_step, dh, 0.f, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, vr, vu, vc);
+    float dar, dau, dac, dx;
+    dh = gru_bwd_step<true>(w, row, first_step, dh, 0.f, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, myWxT, dx);
     {                                                    // dx of this step -> layer k-1 (every step of layer k is one of its firing steps)
-      float2 m = make_float2(0.f, 0.f), o = m;
-      half_part_smem(vr, myWxT + (0 * 8) * 2 * HP + i, 2, m, o);
-      half_part_smem(vu, myWxT + (1 * 8) * 2 * HP + i, 2, m, o);
-      half_part_smem(vc, myWxT + (2 * 8) * 2 * HP + i, 2, m, o);
-      const float dx = half_finish(m.x + m.y, o.x + o.y);
       if (grouped_out) {
         const unsigned v = sent + vofs;                  // virtual hand-off index: group = v / HG, ring slot = v % HRS
         const int g = (v / HG) & 1;
@@ -983,21 +1077,28 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
 
   Handoff* hin = k < L - 1 ? &hand[k * nspc + si] : nullptr;        // from layer k+1
   Handoff* hout = k > 0 ? &hand[(k - 1) * nspc + si] : nullptr;     // to layer k-1
-  if (a.whelper[w]) {                                    // layer 1's dx warp
-    wave_bwd_dx_helper(a, i, sWxT, &hand3[si], &hand[0 * nspc + si]);
+  if (a.whelper[w]) {                                    // layer 1's dx warp; also serves layer 0's chunk I/O
+    float* s_st0 = reinterpret_cast<float*>(dsm + sm.l0 + si * bwd_region_bytes(BCH0, BNS0));   // same carve-up as wave_bwd_fast
+    float* s_da0 = s_st0 + BNS0 * (BCH0 + 1) * ST;
+    uint64_t* full0 = reinterpret_cast<uint64_t*>(s_da0 + 2 * BCH0 * G3 + 96);
+    const L0BwdIo io{s_st0, s_da0, full0, a.st[0] + (int64_t)b * a.S[0] * ST, a.da[0] + (int64_t)b * a.S[0] * G3, a.S[0]};
+    wave_bwd_dx_helper(a, i, sWxT, &hand3[si], &hand[0 * nspc + si], io);
     return;
   }
   if (k == 0) {
     unsigned char* reg0 = dsm + sm.l0 + si * bwd_region_bytes(BCH0, BNS0);
-    if (hin == nullptr) wave_bwd_fast<false, false, DBG>(a, 0, b, i, reg0, nullptr, nullptr);
-    else wave_bwd_fast<true, false, DBG>(a, 0, b, i, reg0, hin, nullptr);
+    if (hin == nullptr) wave_bwd_fast<false, false, false, DBG>(a, 0, b, i, reg0, nullptr, nullptr);
+    else wave_bwd_fast<true, false, true, DBG>(a, 0, b, i, reg0, hin, nullptr);
   } else if (k == 1) {
     unsigned char* reg1 = dsm + sm.l1 + si * bwd_region_bytes(BCH0, BNS0);
-    if (hin == nullptr) wave_bwd_fast<false, true, DBG>(a, 1, b, i, reg1, nullptr, &hand3[si]);
-    else wave_bwd_fast<true, true, DBG>(a, 1, b, i, reg1, hin, &hand3[si]);
+    if (hin == nullptr) wave_bwd_fast<false, true, false, DBG>(a, 1, b, i, reg1, nullptr, &hand3[si]);
+    else wave_bwd_fast<true, true, false, DBG>(a, 1, b, i, reg1, hin, &hand3[si]);
+  } else if (k == 2) {
+    wave_bwd_layer<BCH2, BNSK, DBG>(a, k, b, i, dsm + sm.l2 + si * bwd_region_bytes(BCH2, BNSK), hin, hout,
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * 2 * HP);
   } else {
-    wave_bwd_layer<BCHK, BNSK, DBG>(a, k, b, i, dsm + sm.lk + ((k - 2) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
-                               sWxT + (size_t)(k - 1) * 3 * 8 * 2 * HP);
+    wave_bwd_layer<BCHK, BNSK, DBG>(a, k, b, i, dsm + sm.lk + ((k - 3) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * 2 * HP);
   }
 }
 
