@@ -102,13 +102,16 @@ __device__ __forceinline__ Part half_part(const float4 (&v)[4], const HalfW& w, 
   Part p; p.m = (m0.x + m1.x) + (m0.y + m1.y); p.o = (o0.x + o1.x) + (o0.y + o1.y);
   return p;
 }
-// same with the weights in shared memory: wq = base + lane, element (q, which) at wq[(q * qstride + which) * HP]
-__device__ __forceinline__ void half_part_smem(const float4 (&v)[4], const float2* wq, int qstride, float2& m, float2& o) {
+// same with the weights in shared memory, one float4 per K-pair: (mine.x, mine.y, other.x, other.y) at wq[pair * pstride]
+// (wq already includes the lane).  One LDS.128 feeds two FFMA2: with ~30 free registers next to the 96 of the recurrent
+// weights, ptxas otherwise serialises load -> use pairs (r1 v9: 24 of them back to back in the backward step of layer 2).
+__device__ __forceinline__ void half_part_smem(const float4 (&v)[4], const float4* wq, int pstride, float2& m, float2& o) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    const float4 wa = wq[(2 * q) * pstride], wb = wq[(2 * q + 1) * pstride];
     const float2 xa = make_float2(v[q].x, v[q].y), xb = make_float2(v[q].z, v[q].w);
-    m = ffma2(xa, wq[((2 * q) * qstride + 0) * HP], m); o = ffma2(xa, wq[((2 * q) * qstride + 1) * HP], o);
-    m = ffma2(xb, wq[((2 * q + 1) * qstride + 0) * HP], m); o = ffma2(xb, wq[((2 * q + 1) * qstride + 1) * HP], o);
+    m = ffma2(xa, make_float2(wa.x, wa.y), m); o = ffma2(xa, make_float2(wa.z, wa.w), o);
+    m = ffma2(xb, make_float2(wb.x, wb.y), m); o = ffma2(xb, make_float2(wb.z, wb.w), o);
   }
 }
 __device__ __forceinline__ float half_finish(float mine, float other) { return mine + __shfl_xor_sync(0xffffffffu, other, 1); }
@@ -190,7 +193,7 @@ struct WaveSmem {
   int r0, r1;                      // per-warp region sizes: layer 0 / layers >= 1
   __host__ __device__ WaveSmem(int L, int nspc) {
     int off = 0;
-    wx = off; off += (L - 1) * 8 * 3 * 2 * HP * 8;         // float2 [q][g][mine|other][lane] per layer >= 1
+    wx = off; off += (L - 1) * 8 * 3 * HP * 16;            // float4 [q][g][lane] = (mine pair | other pair) per layer >= 1
     bx = off; off += (L - 1) * G3 * 4;
     off = (off + 127) & ~127;
     hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
@@ -400,7 +403,7 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool GROUPED_IN>
 __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, int j, float* s_out, float* sh_rh, float* sh_h,
-                                               const float2* myWx, const float* myBx, Handoff* hin, Handoff* hout) {
+                                               const float4* myWx, const float* myBx, Handoff* hin, Handoff* hout) {
   constexpr int CH = WCH;
   const int S = a.S[k], period = a.P[k];
   FwdW w;
@@ -425,9 +428,9 @@ __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, 
     load_vec_half(v, hin->ring[slot_in], j);
     float2 m0 = make_float2(myBx[j], 0.f), m1 = make_float2(myBx[HP + j], 0.f), m2 = make_float2(myBx[2 * HP + j], 0.f);
     float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0;
-    half_part_smem(v, myWx + 0 * 2 * HP + j, 6, m0, o0);
-    half_part_smem(v, myWx + 1 * 2 * HP + j, 6, m1, o1);
-    half_part_smem(v, myWx + 2 * 2 * HP + j, 6, m2, o2);
+    half_part_smem(v, myWx + 0 * HP + j, 3 * HP, m0, o0);
+    half_part_smem(v, myWx + 1 * HP + j, 3 * HP, m1, o1);
+    half_part_smem(v, myWx + 2 * HP + j, 3 * HP, m2, o2);
     ar = half_finish(m0.x + m0.y, o0.x + o0.y);
     au = half_finish(m1.x + m1.y, o1.x + o1.y);
     ac = half_finish(m2.x + m2.y, o2.x + o2.y);
@@ -485,13 +488,16 @@ __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, 
 
 // Helper warp of layer 1: applies W_x^(1) (pre-scaled, in registers) to every hand-off of layer 0 and delivers the projected
 // rows to layer 1 in chunks of BLK, so that layer 1 runs layer 0's loop at half its rate.
-__device__ __forceinline__ void wave_proj_helper(int n, int j, const float2* myWx, const float* myBx, Handoff* hin, InRing* inr,
+__device__ __forceinline__ void wave_proj_helper(int n, int j, const float4* myWx, const float* myBx, Handoff* hin, InRing* inr,
                                                  const L0Io io) {
   HalfW w[3];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { w[g].m[q] = myWx[((q * 3 + g) * 2 + 0) * HP + j]; w[g].o[q] = myWx[((q * 3 + g) * 2 + 1) * HP + j]; }
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = myWx[(q * 3 + g) * HP + j];
+      w[g].m[q] = make_float2(t.x, t.y); w[g].o[q] = make_float2(t.z, t.w);
+    }
   const float b0 = myBx[j], b1 = myBx[HP + j], b2 = myBx[2 * HP + j];
   for (unsigned idx = 0; idx < (unsigned)n; ++idx) {
     const int slot = idx & (HRS - 1), g = (idx / HG) & 1;
@@ -545,19 +551,20 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
   const int b = blockIdx.x * nspc + si;
   const WaveSmem sm(L, nspc);
   InRing* inr = reinterpret_cast<InRing*>(dsm + sm.hand3);
-  float2* sWx = reinterpret_cast<float2*>(dsm + sm.wx);
+  float4* sWx = reinterpret_cast<float4*>(dsm + sm.wx);
   float* sBx = reinterpret_cast<float*>(dsm + sm.bx);
   Handoff* hand = reinterpret_cast<Handoff*>(dsm + sm.hand);
 
-  // ---- CTA setup: W_x / b_x of layers >= 1 into shared memory, K-half layout [q][g][mine|other][lane], times the log2(e)
+  // ---- CTA setup: W_x / b_x of layers >= 1 into shared memory, K-half layout [q][g][lane] x (mine | other), times the log2(e)
   // factor of their gate; hand-off barriers ----
-  for (int e = tid; e < (L - 1) * 8 * 3 * 2 * HP; e += blockDim.x) {
-    const int kk = 1 + e / (8 * 3 * 2 * HP), r = e % (8 * 3 * 2 * HP);
-    const int q = r / (3 * 2 * HP), g = (r / (2 * HP)) % 3, which = (r / HP) & 1, lane = r % HP;
-    const int kr = 16 * (lane & 1) + 2 * q, col = g * HP + (which ? lane ^ 1 : lane);
+  for (int e = tid; e < (L - 1) * 8 * 3 * HP; e += blockDim.x) {
+    const int kk = 1 + e / (8 * 3 * HP), r = e % (8 * 3 * HP);
+    const int q = r / (3 * HP), g = (r / HP) % 3, lane = r % HP;
+    const int kr = 16 * (lane & 1) + 2 * q, cm = g * HP + lane, co = g * HP + (lane ^ 1);
     const float sc = g == 2 ? kTwoLog2e : kNegLog2e;
     const float* Wx = a.pw + a.Wx[kk];                   // [32][96]
-    sWx[e] = make_float2(sc * __ldg(Wx + kr * G3 + col), sc * __ldg(Wx + (kr + 1) * G3 + col));
+    sWx[e] = make_float4(sc * __ldg(Wx + kr * G3 + cm), sc * __ldg(Wx + (kr + 1) * G3 + cm),
+                         sc * __ldg(Wx + kr * G3 + co), sc * __ldg(Wx + (kr + 1) * G3 + co));
   }
   for (int e = tid; e < (L - 1) * G3; e += blockDim.x)
     sBx[e] = (e % G3 >= 2 * HP ? kTwoLog2e : kNegLog2e) * __ldg(a.pw + a.bx[1 + e / G3] + e % G3);
@@ -603,7 +610,7 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
     float* sh_h = sh_rh + 32;
     sh_h[j] = 0.f;
     __syncwarp();
-    const float2* myWx = sWx + (size_t)(k - 1) * 8 * 3 * 2 * HP;
+    const float4* myWx = sWx + (size_t)(k - 1) * 8 * 3 * HP;
     const float* myBx = sBx + (k - 1) * G3;
     if (k == 1) {
       if (hout == nullptr) h = wave_layer_fast<false, false>(a, 1, b, j, nullptr, nullptr, &inr[si], s_out, sh_rh, sh_h, nullptr);
@@ -671,7 +678,7 @@ struct WaveBwdSmem {
   int wxt, hand, hand3, l0, l1, l2, lk, total;
   __host__ __device__ WaveBwdSmem(int L, int nspc) {
     int off = 0;
-    wxt = off; off += (L - 1) * 3 * 8 * 2 * HP * 8;        // float2 [g][q][mine|other][lane] per layer >= 1
+    wxt = off; off += (L - 1) * 3 * 8 * HP * 16;           // float4 [g][q][lane] = (mine pair | other pair) per layer >= 1
     off = (off + 127) & ~127;
     hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
     off = (off + 127) & ~127;
@@ -704,7 +711,7 @@ __device__ __forceinline__ void load_bwd_weights(BwdW& w, const float* WhT /*[3]
 template <bool WITH_DX>
 __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, bool first_step, float dh, float add, int i,
                                               float* sh_c, float* sh_r, float* sh_u, float* orow, float& dar, float& dau,
-                                              float& dac, const float2* myWxT, float& dx) {
+                                              float& dac, const float4* myWxT, float& dx) {
   const float hp = first_step ? 0.f : row[0];            // zero state before step 0
   const float r = row[ST + HP], u = row[ST + 2 * HP], c = row[ST + 3 * HP];
   const float omu = 1.f - u;
@@ -715,26 +722,40 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
   sh_c[i] = dac;
   sh_u[i] = dau;
   __syncwarp();
-  float4 v[4], vu[4];
+  float4 v[4];
   load_vec_half(v, sh_c, i);
-  load_vec_half(vu, sh_u, i);
+  if (!WITH_DX) {                                        // latency-tuned order (layers 0 and 1): da_u's mat-vec fills the bubbles
+    float4 vu[4];
+    load_vec_half(vu, sh_u, i);
+    const Part pc = half_part(v, w.c, 0.f);
+    const float drh = half_finish(pc.m, pc.o);           // (da_c Wc^T)[Din + i]
+    dar = drh * gr;
+    sh_r[i] = dar;
+    __syncwarp();
+    load_vec_half(v, sh_r, i);
+    const Part pu = half_part(vu, w.u, fmaf(dh, u, add));
+    const Part pr = half_part(v, w.r, drh * r);
+    orow[0] = dar; orow[HP] = dau; orow[2 * HP] = dac;
+    return half_finish(pr.m + pu.m, pr.o + pu.o);        // gradient wrt h_{s-1} (+ the share of the layer above)
+  }
+  // layers >= 2: one broadcast vector live at a time, so that the W_x^T loads (shared memory) can be batched in the ~35
+  // registers next to the recurrent weights
+  float2 xm0 = make_float2(0.f, 0.f), xo0 = xm0, xm1 = xm0, xo1 = xm0, xm2 = xm0, xo2 = xm0;
   const Part pc = half_part(v, w.c, 0.f);
-  const float drh = half_finish(pc.m, pc.o);             // (da_c Wc^T)[Din + i]
+  const float drh = half_finish(pc.m, pc.o);
   dar = drh * gr;
   sh_r[i] = dar;
   __syncwarp();
-  float2 xm0 = make_float2(0.f, 0.f), xo0 = xm0, xm1 = xm0, xo1 = xm0, xm2 = xm0, xo2 = xm0;
-  if (WITH_DX) half_part_smem(v, myWxT + (2 * 8) * 2 * HP + i, 2, xm2, xo2);    // rows 64..95 of W_x^T: da_c
+  half_part_smem(v, myWxT + (2 * 8) * HP + i, HP, xm2, xo2);                    // rows 64..95 of W_x^T: da_c
+  load_vec_half(v, sh_u, i);
+  const Part pu = half_part(v, w.u, fmaf(dh, u, add));
+  half_part_smem(v, myWxT + (1 * 8) * HP + i, HP, xm1, xo1);                    // rows 32..63: da_u
   load_vec_half(v, sh_r, i);
-  const Part pu = half_part(vu, w.u, fmaf(dh, u, add));  // off the chain
-  if (WITH_DX) half_part_smem(vu, myWxT + (1 * 8) * 2 * HP + i, 2, xm1, xo1);   // rows 32..63: da_u
   const Part pr = half_part(v, w.r, drh * r);
+  half_part_smem(v, myWxT + (0 * 8) * HP + i, HP, xm0, xo0);                    // rows 0..31: da_r
   orow[0] = dar; orow[HP] = dau; orow[2 * HP] = dac;
-  const float dhn = half_finish(pr.m + pu.m, pr.o + pu.o);   // gradient wrt h_{s-1} (+ the share of the layer above)
-  if (WITH_DX) {
-    half_part_smem(v, myWxT + (0 * 8) * 2 * HP + i, 2, xm0, xo0);               // rows 0..31: da_r
-    dx = half_finish(((xm0.x + xm0.y) + (xm1.x + xm1.y)) + (xm2.x + xm2.y), ((xo0.x + xo0.y) + (xo1.x + xo1.y)) + (xo2.x + xo2.y));
-  }
+  const float dhn = half_finish(pr.m + pu.m, pr.o + pu.o);
+  dx = half_finish(((xm0.x + xm0.y) + (xm1.x + xm1.y)) + (xm2.x + xm2.y), ((xo0.x + xo0.y) + (xo1.x + xo1.y)) + (xo2.x + xo2.y));
   return dhn;
 }
 
@@ -870,7 +891,7 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
 
 // Helper warp of layer 1: dx = da W_x^(1)T for every step of layer 1, W_x^T in registers, handed to layer 0 in groups of
 // HG rows aligned with layer 0's chunks.
-__device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, const float2* myWxT, Handoff3* hda, Handoff* hout,
+__device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, const float4* myWxT, Handoff3* hda, Handoff* hout,
                                                    const L0BwdIo io) {
   constexpr int CH = BCH0, NS = BNS0;
   const int nch0 = (io.S + CH - 1) / CH;
@@ -890,7 +911,7 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { w[g].m[q] = myWxT[((g * 8 + q) * 2 + 0) * HP + i]; w[g].o[q] = myWxT[((g * 8 + q) * 2 + 1) * HP + i]; }
+    for (int q = 0; q < 8; ++q) { const float4 t = myWxT[(g * 8 + q) * HP + i]; w[g].m[q] = make_float2(t.x, t.y); w[g].o[q] = make_float2(t.z, t.w); }
   const unsigned n = (unsigned)a.S[1], vofs = group_vofs(a.S[0]);
   for (unsigned idx = 0; idx < n; ++idx) {
     const int slot = idx & (HRS - 1);
@@ -930,7 +951,7 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
 // except towards layer 1 (k == 2), which consumes groups.
 template <int CH, int NS, bool DBG>
 __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int b, int i, unsigned char* reg, Handoff* hin,
-                                               Handoff* hout, const float2* myWxT) {
+                                               Handoff* hout, const float4* myWxT) {
   long long w_in = 0, w_out = 0, w_tma = 0;               // DBG: cycles blocked on hand-off in / out and on the TMA ring
   const bool dbg = DBG && blockIdx.x == 0;
   const long long t_start = DBG ? clock64() : 0;
@@ -971,7 +992,9 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
   const bool grouped_out = k == 2;                       // layer 1 consumes through wave_bwd_fast
   const unsigned vofs = grouped_out ? group_vofs(a.S[1]) : 0u;
 
+  long long q_hin = 0, q_step = 0, q_out = 0;             // DBG: cycles in the hand-in block, the step proper, the hand-down block
   auto step = [&](const float* row, float* orow, bool first_step) {
+    const long long c0 = dbg ? clock64() : 0;
     if (hin != nullptr && --to_fire == 0) {              // this step fed layer k+1 in the forward pass
       to_fire = period;
       const int slot = got & (HRS - 1);
@@ -982,7 +1005,9 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
       if (i == 0) mbar_arrive(&hin->empty[slot]);
     }
     float dar, dau, dac, dx;
+    const long long c1 = dbg ? clock64() : 0;
     dh = gru_bwd_step<true>(w, row, first_step, dh, 0.f, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, myWxT, dx);
+    const long long c2 = dbg ? clock64() + (long long)(dx == 12345.f) : 0;
     {                                                    // dx of this step -> layer k-1 (every step of layer k is one of its firing steps)
       if (grouped_out) {
         const unsigned v = sent + vofs;                  // virtual hand-off index: group = v / HG, ring slot = v % HRS
@@ -1004,6 +1029,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
       }
     }
     __syncwarp();                                        // sh_c / sh_r / sh_u free for the next step
+    if (dbg) { const long long c3 = clock64(); q_hin += c1 - c0; q_step += c2 - c1; q_out += c3 - c2; }
   };
 
   for (int it = 0; it < nch; ++it) {
@@ -1035,8 +1061,8 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
   if (i == 0) bulk_wait_read<0>();
   __syncwarp();
   if (dbg && i == 0 && b == 0)
-    printf("wave_bwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld\n", k, S,
-           clock64() - t_start, (clock64() - t_start) / S, w_in, w_out, w_tma);
+    printf("wave_bwd layer %d: steps %d total %lld cyc (%lld/step)  wait_in %lld  wait_out %lld  wait_tma %lld  [hand-in %lld  step %lld  hand-down %lld]\n", k, S,
+           clock64() - t_start, (clock64() - t_start) / S, w_in, w_out, w_tma, q_hin, q_step, q_out);
 }
 
 // Registers are partitioned per SM sub-partition (16 K each): 12 warps = 3 per SMSP = at most 168 per thread.
@@ -1049,17 +1075,18 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
   const int k = a.wlayer[w], si = a.wsample[w];         // see plan_warps()
   const int b = blockIdx.x * nspc + si;
   const WaveBwdSmem sm(L, nspc);
-  float2* sWxT = reinterpret_cast<float2*>(dsm + sm.wxt);
+  float4* sWxT = reinterpret_cast<float4*>(dsm + sm.wxt);
   Handoff* hand = reinterpret_cast<Handoff*>(dsm + sm.hand);
   Handoff3* hand3 = reinterpret_cast<Handoff3*>(dsm + sm.hand3);
 
-  // ---- CTA setup: W_x^T of layers >= 1 in the K-half layout [g][q][mine|other][lane] ----
-  for (int e = tid; e < (L - 1) * 3 * 8 * 2 * HP; e += blockDim.x) {
-    const int kk = 1 + e / (3 * 8 * 2 * HP), r = e % (3 * 8 * 2 * HP);
-    const int g = r / (8 * 2 * HP), q = (r / (2 * HP)) % 8, which = (r / HP) & 1, lane = r % HP;
-    const int n = g * HP + 16 * (lane & 1) + 2 * q, col = which ? lane ^ 1 : lane;
+  // ---- CTA setup: W_x^T of layers >= 1 in the K-half layout [g][q][lane] x (mine | other) ----
+  for (int e = tid; e < (L - 1) * 3 * 8 * HP; e += blockDim.x) {
+    const int kk = 1 + e / (3 * 8 * HP), r = e % (3 * 8 * HP);
+    const int g = r / (8 * HP), q = (r / HP) % 8, lane = r % HP;
+    const int n = g * HP + 16 * (lane & 1) + 2 * q;
     const float* WxT = a.pw + a.WxT[kk];                 // [96][32]
-    sWxT[e] = make_float2(__ldg(WxT + n * HP + col), __ldg(WxT + (n + 1) * HP + col));
+    sWxT[e] = make_float4(__ldg(WxT + n * HP + lane), __ldg(WxT + (n + 1) * HP + lane),
+                          __ldg(WxT + n * HP + (lane ^ 1)), __ldg(WxT + (n + 1) * HP + (lane ^ 1)));
   }
   for (int e = tid; e < (L - 1) * nspc * HRS; e += blockDim.x) {
     mbar_init(&hand[e / HRS].full[e % HRS], 1);
@@ -1095,10 +1122,10 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     else wave_bwd_fast<true, true, false, DBG>(a, 1, b, i, reg1, hin, &hand3[si]);
   } else if (k == 2) {
     wave_bwd_layer<BCH2, BNSK, DBG>(a, k, b, i, dsm + sm.l2 + si * bwd_region_bytes(BCH2, BNSK), hin, hout,
-                                    sWxT + (size_t)(k - 1) * 3 * 8 * 2 * HP);
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP);
   } else {
     wave_bwd_layer<BCHK, BNSK, DBG>(a, k, b, i, dsm + sm.lk + ((k - 3) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
-                                    sWxT + (size_t)(k - 1) * 3 * 8 * 2 * HP);
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP);
   }
 }
 
