@@ -44,6 +44,16 @@ constexpr int BLK = 8;        // steps per block of the latency-critical loops =
 #ifndef HPMN_GUNR
 #define HPMN_GUNR 1
 #endif
+#ifndef HPMN_CSMEM_FWD
+#define HPMN_CSMEM_FWD 1
+#endif
+#ifndef HPMN_CSMEM_BWD
+#define HPMN_CSMEM_BWD 0
+#endif
+// layers >= 2 read the candidate gate's recurrent weights from shared memory instead of holding them in registers: 32 more
+// registers for batching their other shared-memory weight loads.  Measured (XLong, B=256): forward 0.294 -> 0.292 ms; backward
+// 0.266 -> 0.290 ms (layer 2's step gets 30 % shorter, but the extra LSU traffic slows the co-critical layers 0 and 1) => off.
+constexpr bool CS_FWD = HPMN_CSMEM_FWD != 0, CS_BWD = HPMN_CSMEM_BWD != 0;
 constexpr int FUNR = HPMN_FUNR, BUNR = HPMN_BUNR, GUNR = HPMN_GUNR;   // GUNR: the loops of the layers off the critical path
 constexpr int WAVE_MAX_L = 10;
 
@@ -54,9 +64,9 @@ struct Handoff {                   // layer k -> k+1 (fwd) / k+1 -> k (bwd) of o
   uint64_t full[HRS], empty[HRS];  // per-slot protocol (layers off the critical path)
   uint64_t gfull[2], gempty[2];    // group protocol: one barrier round trip per HG rows
 };
-struct Handoff3 {                  // projected input (fwd) / da row (bwd) of layer 1: 96 floats per slot
+struct Handoff3 {                  // da rows of layer 1 on their way to the dx helper (bwd): 96 floats per slot, groups of HG rows
   float ring[HRS][G3];
-  uint64_t full[HRS], empty[HRS];
+  uint64_t gfull[2], gempty[2];
 };
 
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool timed) {
@@ -189,11 +199,12 @@ struct InRing {                    // helper -> layer 1: two chunks of BLK proje
 
 // shared-memory plan (bytes)
 struct WaveSmem {
-  int wx, bx, hand, hand3, l0, lk, total;
+  int wx, whc, bx, hand, hand3, l0, lk, total;
   int r0, r1;                      // per-warp region sizes: layer 0 / layers >= 1
   __host__ __device__ WaveSmem(int L, int nspc) {
     int off = 0;
     wx = off; off += (L - 1) * 8 * 3 * HP * 16;            // float4 [q][g][lane] = (mine pair | other pair) per layer >= 1
+    whc = off; off += (L > 2 ? L - 2 : 0) * 8 * HP * 16;   // candidate-gate recurrent weights of layers >= 2, float4 [q][lane]
     bx = off; off += (L - 1) * G3 * 4;
     off = (off + 127) & ~127;
     hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
@@ -224,8 +235,11 @@ __device__ __forceinline__ void load_fwd_weights(FwdW& w, const float* Wh /*[3][
 // One GRU step (util.py:81-110 minus :108) of the (layer, sample) this warp owns.  ar|au|ac: this lane's projected inputs,
 // already multiplied by the log2(e) factors; sh_h holds h_{t-1} (all lanes), out is this lane's column of the state row.
 // The caller issues the __syncwarp() that closes the step (after its own stores).
+// C_SMEM (layers >= 2): the candidate gate's recurrent weights come from shared memory (wc_s: float4 [8][lane], pre-scaled)
+// instead of registers -- 32 registers more for batching these layers' shared-memory weight loads.
+template <bool C_SMEM>
 __device__ __forceinline__ float gru_fwd_step(const FwdW& w, float ar, float au, float ac, float h, int j, float* sh_h,
-                                              float* sh_rh, float* out) {
+                                              float* sh_rh, float* out, const float4* wc_s) {
   float4 v[4];
   load_vec_half(v, sh_h, j);
   const Part pr = half_part(v, w.r, ar), pu = half_part(v, w.u, au);
@@ -235,7 +249,14 @@ __device__ __forceinline__ float gru_fwd_step(const FwdW& w, float ar, float au,
   __syncwarp();
   load_vec_half(v, sh_rh, j);
   const float u = rcp_ftz(1.0f + ex2_ftz(su));
-  const Part pc = half_part(v, w.c, ac);
+  Part pc;
+  if (C_SMEM) {
+    float2 m = make_float2(ac, 0.f), o = make_float2(0.f, 0.f);
+    half_part_smem(v, wc_s + j, HP, m, o);
+    pc.m = m.x + m.y; pc.o = o.x + o.y;
+  } else {
+    pc = half_part(v, w.c, ac);
+  }
   const float omu = 1.0f - u, uh = u * h;
   const float x2l = half_finish(pc.m, pc.o);             // 2 log2(e) x
   const float qv = rcp_ftz(1.0f + ex2_ftz(x2l));         // tanh(x) = 1 - 2 qv                  util.py:107
@@ -302,8 +323,8 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
   float h = 0.f;                                         // zero_state, code/rnn.py:588 (sh_h starts as the zero row)
 
   auto step = [&](const float* in, float* out) {
-    if (TMA_IN) h = gru_fwd_step(w, in[0] * kNegLog2e, in[HP] * kNegLog2e, in[2 * HP] * kTwoLog2e, h, j, sh_h, sh_rh, out);
-    else h = gru_fwd_step(w, in[0], in[HP], in[2 * HP], h, j, sh_h, sh_rh, out);
+    if (TMA_IN) h = gru_fwd_step<false>(w, in[0] * kNegLog2e, in[HP] * kNegLog2e, in[2 * HP] * kTwoLog2e, h, j, sh_h, sh_rh, out, nullptr);
+    else h = gru_fwd_step<false>(w, in[0], in[HP], in[2 * HP], h, j, sh_h, sh_rh, out, nullptr);
   };
 
   for (int c = 0; c < nch; ++c) {
@@ -403,11 +424,14 @@ __device__ __forceinline__ float wave_layer_fast(const WaveArgs& a, int k, int b
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool GROUPED_IN>
 __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, int j, float* s_out, float* sh_rh, float* sh_h,
-                                               const float4* myWx, const float* myBx, Handoff* hin, Handoff* hout) {
+                                               const float4* myWx, const float* myBx, const float4* myWhc, Handoff* hin,
+                                               Handoff* hout) {
   constexpr int CH = WCH;
   const int S = a.S[k], period = a.P[k];
-  FwdW w;
-  load_fwd_weights(w, a.pw + a.Wh[k], j);
+  FwdW w;                                                // r and u in registers, c from shared memory (myWhc)
+  load_half(w.r, a.pw + a.Wh[k], j, kNegLog2e);
+  load_half(w.u, a.pw + a.Wh[k] + HP * HP, j, kNegLog2e);
+  if (!CS_FWD) load_half(w.c, a.pw + a.Wh[k] + 2 * HP * HP, j, kTwoLog2e);
   float* so = a.st[k] + (int64_t)b * S * ST;
   const int nch = (S + CH - 1) / CH;
 
@@ -445,7 +469,7 @@ __device__ __forceinline__ float wave_layer_up(const WaveArgs& a, int k, int b, 
     const float ar = nar, au = nau, ac = nac;
     ++s_glob;
     if (s_glob < (unsigned)S) project(s_glob, nar, nau, nac);
-    h = gru_fwd_step(w, ar, au, ac, h, j, sh_h, sh_rh, orow + j);
+    h = gru_fwd_step<CS_FWD>(w, ar, au, ac, h, j, sh_h, sh_rh, orow + j, myWhc);
     if (hout != nullptr && --to_fire == 0) {             // this step feeds layer k+1
       to_fire = period;
       const int slot_out = fired & (HRS - 1);
@@ -566,6 +590,14 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
     sWx[e] = make_float4(sc * __ldg(Wx + kr * G3 + cm), sc * __ldg(Wx + (kr + 1) * G3 + cm),
                          sc * __ldg(Wx + kr * G3 + co), sc * __ldg(Wx + (kr + 1) * G3 + co));
   }
+  float4* sWhc = reinterpret_cast<float4*>(dsm + sm.whc);
+  for (int e = tid; e < (L - 2) * 8 * HP; e += blockDim.x) {
+    const int kk = 2 + e / (8 * HP), q = (e / HP) % 8, lane = e % HP;
+    const int kr = 16 * (lane & 1) + 2 * q;
+    const float* Wc = a.pw + a.Wh[kk] + 2 * HP * HP;     // [32 i][32 j]
+    sWhc[e] = make_float4(kTwoLog2e * __ldg(Wc + kr * HP + lane), kTwoLog2e * __ldg(Wc + (kr + 1) * HP + lane),
+                          kTwoLog2e * __ldg(Wc + kr * HP + (lane ^ 1)), kTwoLog2e * __ldg(Wc + (kr + 1) * HP + (lane ^ 1)));
+  }
   for (int e = tid; e < (L - 1) * G3; e += blockDim.x)
     sBx[e] = (e % G3 >= 2 * HP ? kTwoLog2e : kNegLog2e) * __ldg(a.pw + a.bx[1 + e / G3] + e % G3);
   for (int e = tid; e < (L - 1) * nspc * HRS; e += blockDim.x) {
@@ -616,9 +648,9 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
       if (hout == nullptr) h = wave_layer_fast<false, false>(a, 1, b, j, nullptr, nullptr, &inr[si], s_out, sh_rh, sh_h, nullptr);
       else h = wave_layer_fast<false, true>(a, 1, b, j, nullptr, nullptr, &inr[si], s_out, sh_rh, sh_h, hout);
     } else if (k == 2) {
-      h = wave_layer_up<true>(a, k, b, j, s_out, sh_rh, sh_h, myWx, myBx, hin, hout);
+      h = wave_layer_up<true>(a, k, b, j, s_out, sh_rh, sh_h, myWx, myBx, sWhc + (size_t)(k - 2) * 8 * HP, hin, hout);
     } else {
-      h = wave_layer_up<false>(a, k, b, j, s_out, sh_rh, sh_h, myWx, myBx, hin, hout);
+      h = wave_layer_up<false>(a, k, b, j, s_out, sh_rh, sh_h, myWx, myBx, sWhc + (size_t)(k - 2) * 8 * HP, hin, hout);
     }
   }
   if (j < a.H) a.memory[((int64_t)b * L + k) * a.H + j] = h;   // final state -> memory slot k, hpmn.py:121
@@ -629,7 +661,7 @@ bool launch_wave_fwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   if (d.L > WAVE_MAX_L || !wave_supported(d.L, d.P)) return false;
   const int nspc = d.L <= 5 ? 2 : 1;                     // register budget: 12 warps x 32 x 168
   const WaveSmem sm(d.L, nspc);
-  if (sm.total > 220 * 1024) return false;
+  if (sm.total > 227 * 1024) return false;   // opt-in maximum of dynamic shared memory per CTA on sm_100
   WaveArgs a; memset(&a, 0, sizeof(a));
   a.proj0 = proj0; a.pw = pw; a.memory = memory;
   a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
@@ -675,10 +707,11 @@ __host__ __device__ constexpr int bwd_region_bytes(int ch, int ns) {
 }
 
 struct WaveBwdSmem {
-  int wxt, hand, hand3, l0, l1, l2, lk, total;
+  int wxt, whc, hand, hand3, l0, l1, l2, lk, total;
   __host__ __device__ WaveBwdSmem(int L, int nspc) {
     int off = 0;
     wxt = off; off += (L - 1) * 3 * 8 * HP * 16;           // float4 [g][q][lane] = (mine pair | other pair) per layer >= 1
+    whc = off; off += (L > 2 ? L - 2 : 0) * 8 * HP * 16;   // candidate-gate W_h^T of layers >= 2, float4 [q][lane]
     off = (off + 127) & ~127;
     hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
     off = (off + 127) & ~127;
@@ -711,7 +744,7 @@ __device__ __forceinline__ void load_bwd_weights(BwdW& w, const float* WhT /*[3]
 template <bool WITH_DX>
 __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, bool first_step, float dh, float add, int i,
                                               float* sh_c, float* sh_r, float* sh_u, float* orow, float& dar, float& dau,
-                                              float& dac, const float4* myWxT, float& dx) {
+                                              float& dac, const float4* myWxT, const float4* myWhcT, float& dx) {
   const float hp = first_step ? 0.f : row[0];            // zero state before step 0
   const float r = row[ST + HP], u = row[ST + 2 * HP], c = row[ST + 3 * HP];
   const float omu = 1.f - u;
@@ -741,8 +774,15 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
   // layers >= 2: one broadcast vector live at a time, so that the W_x^T loads (shared memory) can be batched in the ~35
   // registers next to the recurrent weights
   float2 xm0 = make_float2(0.f, 0.f), xo0 = xm0, xm1 = xm0, xo1 = xm0, xm2 = xm0, xo2 = xm0;
-  const Part pc = half_part(v, w.c, 0.f);
-  const float drh = half_finish(pc.m, pc.o);
+  float2 cm = xm0, co = xm0;
+  float drh;
+  if (CS_BWD) {
+    half_part_smem(v, myWhcT + i, HP, cm, co);           // candidate-gate W_h^T from shared memory (see gru_fwd_step, C_SMEM)
+    drh = half_finish(cm.x + cm.y, co.x + co.y);
+  } else {
+    const Part pc = half_part(v, w.c, 0.f);
+    drh = half_finish(pc.m, pc.o);
+  }
   dar = drh * gr;
   sh_r[i] = dar;
   __syncwarp();
@@ -815,14 +855,16 @@ __device__ __forceinline__ void wave_bwd_fast(const WaveBwdArgs& a, int k, int b
 
   auto step = [&](const float* row, float* orow, bool first_step, float add) {
     float dar, dau, dac, dx_unused;
-    dh = gru_bwd_step<false>(w, row, first_step, dh, add, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, nullptr, dx_unused);
+    dh = gru_bwd_step<false>(w, row, first_step, dh, add, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, nullptr, nullptr, dx_unused);
     if (OUT_DA) {                                        // every step of layer 1 fed a firing step of layer 0: da row -> helper
-      const int slot = sent & (HRS - 1);
-      if (sent >= HRS) mbar_wait_t(&hda->empty[slot], (sent / HRS - 1) & 1u, w_out, dbg);
+      const int slot = sent & (HRS - 1), g = (sent / HG) & 1;
+      if ((sent & (HG - 1)) == 0 && sent >= HRS) mbar_wait_t(&hda->gempty[g], (sent / HRS - 1) & 1u, w_out, dbg);
       hda->ring[slot][i] = dar; hda->ring[slot][HP + i] = dau; hda->ring[slot][2 * HP + i] = dac;
       ++sent;
-      __syncwarp();
-      if (i == 0) mbar_arrive(&hda->full[slot]);
+      if ((sent & (HG - 1)) == 0 || sent == (unsigned)S) {   // one barrier round trip per HG rows
+        __syncwarp();
+        if (i == 0) mbar_arrive(&hda->gfull[g]);
+      }
     }
     __syncwarp();                                        // sh_c / sh_r / sh_u free for the next step
   };
@@ -914,8 +956,8 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
     for (int q = 0; q < 8; ++q) { const float4 t = myWxT[(g * 8 + q) * HP + i]; w[g].m[q] = make_float2(t.x, t.y); w[g].o[q] = make_float2(t.z, t.w); }
   const unsigned n = (unsigned)a.S[1], vofs = group_vofs(a.S[0]);
   for (unsigned idx = 0; idx < n; ++idx) {
-    const int slot = idx & (HRS - 1);
-    mbar_wait(&hda->full[slot], (idx / HRS) & 1u);
+    const int slot = idx & (HRS - 1), gi = (idx / HG) & 1;
+    if ((idx & (HG - 1)) == 0) mbar_wait(&hda->gfull[gi], (idx / HRS) & 1u);
     float4 v0[4], v1[4], v2[4];
     load_vec_half(v0, hda->ring[slot], i);
     load_vec_half(v1, hda->ring[slot] + HP, i);
@@ -923,7 +965,7 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
     const Part p0 = half_part(v0, w[0], 0.f), p1 = half_part(v1, w[1], 0.f), p2 = half_part(v2, w[2], 0.f);
     const float dx = half_finish((p0.m + p1.m) + p2.m, (p0.o + p1.o) + p2.o);
     __syncwarp();
-    if (i == 0) mbar_arrive(&hda->empty[slot]);          // row consumed
+    if (i == 0 && ((idx & (HG - 1)) == HG - 1 || idx + 1 == n)) mbar_arrive(&hda->gempty[gi]);   // group consumed
     const unsigned v = idx + vofs;                       // virtual hand-off index: group = v / HG, ring slot = v % HRS
     const int g = (v / HG) & 1;
     if ((v & (HG - 1)) == 0 && v >= HRS) {
@@ -951,7 +993,7 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
 // except towards layer 1 (k == 2), which consumes groups.
 template <int CH, int NS, bool DBG>
 __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int b, int i, unsigned char* reg, Handoff* hin,
-                                               Handoff* hout, const float4* myWxT) {
+                                               Handoff* hout, const float4* myWxT, const float4* myWhcT) {
   long long w_in = 0, w_out = 0, w_tma = 0;               // DBG: cycles blocked on hand-off in / out and on the TMA ring
   const bool dbg = DBG && blockIdx.x == 0;
   const long long t_start = DBG ? clock64() : 0;
@@ -965,7 +1007,9 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
   uint64_t* full = reinterpret_cast<uint64_t*>(sh_u + 32);
 
   BwdW w;
-  load_bwd_weights(w, a.pw + a.WhT[k], i);
+  load_half(w.r, a.pw + a.WhT[k], i, 1.f);              // r and u in registers, c from shared memory (myWhcT)
+  load_half(w.u, a.pw + a.WhT[k] + HP * HP, i, 1.f);
+  if (!CS_BWD) load_half(w.c, a.pw + a.WhT[k] + 2 * HP * HP, i, 1.f);
   const float* sb = a.st[k] + (int64_t)b * S * ST;
   float* dab = a.da[k] + (int64_t)b * S * G3;
   const int nch = (S + CH - 1) / CH;
@@ -1006,7 +1050,7 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
     }
     float dar, dau, dac, dx;
     const long long c1 = dbg ? clock64() : 0;
-    dh = gru_bwd_step<true>(w, row, first_step, dh, 0.f, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, myWxT, dx);
+    dh = gru_bwd_step<true>(w, row, first_step, dh, 0.f, i, sh_c, sh_r, sh_u, orow, dar, dau, dac, myWxT, myWhcT, dx);
     const long long c2 = dbg ? clock64() + (long long)(dx == 12345.f) : 0;
     {                                                    // dx of this step -> layer k-1 (every step of layer k is one of its firing steps)
       if (grouped_out) {
@@ -1088,15 +1132,23 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     sWxT[e] = make_float4(__ldg(WxT + n * HP + lane), __ldg(WxT + (n + 1) * HP + lane),
                           __ldg(WxT + n * HP + (lane ^ 1)), __ldg(WxT + (n + 1) * HP + (lane ^ 1)));
   }
+  float4* sWhcT = reinterpret_cast<float4*>(dsm + sm.whc);
+  for (int e = tid; e < (L - 2) * 8 * HP; e += blockDim.x) {
+    const int kk = 2 + e / (8 * HP), q = (e / HP) % 8, lane = e % HP;
+    const int n = 16 * (lane & 1) + 2 * q;
+    const float* WcT = a.pw + a.WhT[kk] + 2 * HP * HP;   // [32 j][32 i]
+    sWhcT[e] = make_float4(__ldg(WcT + n * HP + lane), __ldg(WcT + (n + 1) * HP + lane),
+                           __ldg(WcT + n * HP + (lane ^ 1)), __ldg(WcT + (n + 1) * HP + (lane ^ 1)));
+  }
   for (int e = tid; e < (L - 1) * nspc * HRS; e += blockDim.x) {
     mbar_init(&hand[e / HRS].full[e % HRS], 1);
     mbar_init(&hand[e / HRS].empty[e % HRS], 1);
     if (e % HRS < 2) { mbar_init(&hand[e / HRS].gfull[e % HRS], 1); mbar_init(&hand[e / HRS].gempty[e % HRS], 1); }
   }
   if (L > 1)
-    for (int e = tid; e < nspc * HRS; e += blockDim.x) {
-      mbar_init(&hand3[e / HRS].full[e % HRS], 1);
-      mbar_init(&hand3[e / HRS].empty[e % HRS], 1);
+    for (int e = tid; e < nspc * 2; e += blockDim.x) {
+      mbar_init(&hand3[e / 2].gfull[e % 2], 1);
+      mbar_init(&hand3[e / 2].gempty[e % 2], 1);
     }
   fence_mbar_init();
   __syncthreads();
@@ -1122,10 +1174,10 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     else wave_bwd_fast<true, true, false, DBG>(a, 1, b, i, reg1, hin, &hand3[si]);
   } else if (k == 2) {
     wave_bwd_layer<BCH2, BNSK, DBG>(a, k, b, i, dsm + sm.l2 + si * bwd_region_bytes(BCH2, BNSK), hin, hout,
-                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP);
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP, sWhcT + (size_t)(k - 2) * 8 * HP);
   } else {
     wave_bwd_layer<BCHK, BNSK, DBG>(a, k, b, i, dsm + sm.lk + ((k - 3) * nspc + si) * bwd_region_bytes(BCHK, BNSK), hin, hout,
-                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP);
+                                    sWxT + (size_t)(k - 1) * 3 * 8 * HP, sWhcT + (size_t)(k - 2) * 8 * HP);
   }
 }
 
@@ -1134,7 +1186,7 @@ bool launch_wave_bwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   if (d.L > WAVE_MAX_L || !wave_supported(d.L, d.P)) return false;
   const int nspc = d.L <= 5 ? 2 : 1;
   const WaveBwdSmem sm(d.L, nspc);
-  if (sm.total > 220 * 1024) return false;
+  if (sm.total > 227 * 1024) return false;   // opt-in maximum of dynamic shared memory per CTA on sm_100
   WaveBwdArgs a; memset(&a, 0, sizeof(a));
   a.pw = pw; a.dmemory = dmemory;
   a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
