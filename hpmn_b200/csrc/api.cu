@@ -237,9 +237,7 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
           lx[k] = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
           gWg[k] = grads + p.pl.Wg[k]; gbg[k] = grads + p.pl.bg[k]; gWc[k] = grads + p.pl.Wc[k]; gbc[k] = grads + p.pl.bc[k];
         }
-        static const bool skip_wgrad = getenv("HPMN_DIAG_SKIP_WGRAD") != nullptr;   // timing diagnosis only: wrong gradients
-        if (skip_wgrad) {}
-        else if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, ws)))
+        if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, ws)))
           for (int k = 0; k < d.L; ++k)
             launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], ws);
       }

@@ -128,6 +128,8 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
   __shared__ __align__(16) float sQ[HP];
   __shared__ float sQn[HP];
   __shared__ float sWq[MD * QS], sHm[HP * QS];
+  pdl_trigger();
+  pdl_wait();                                           // launched early (launch_pdl): the wavefront kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
   AttSmem S(dsm, H4);
@@ -259,6 +261,8 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
   __shared__ float sMean[ML], sRed[NT / 32], sW[ML], sDw[ML], sDs[ML], sMean2[ML];
   __shared__ __align__(16) float sDlast[MD], sQ[HP], sDq[HP], sDqin[HP];
   __shared__ float sWq[MD * QS], sHm[HP * QS];
+  pdl_trigger();                                        // the backward wavefront kernel may set itself up while this grid drains
+  pdl_wait();                                           // launched early itself: the head kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
   AttSmem S(dsm, H4);                       // S.Inp holds d(inp); S.Z1 / S.Z2 hold z then dz
@@ -429,7 +433,7 @@ void launch_attn_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
   a.repre = repre; a.w_hop0 = w_hop0; a.scalars = scalars;
   const size_t dsm = AttSmem::bytes(4 * d.H);
   cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-  attn_fwd_kernel<<<d.B, NT, dsm, st>>>(a);
+  launch_pdl(attn_fwd_kernel, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
   ++*L.counter;
 }
 
@@ -440,7 +444,7 @@ void launch_attn_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
   a.drepre = drepre; a.dmemory = dmemory; a.dlast = dlast; a.memory_reg = memory_reg;
   const size_t dsm = AttSmem::bytes(4 * d.H);
   cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-  attn_bwd_kernel<<<d.B, NT, dsm, st>>>(a);
+  launch_pdl(attn_bwd_kernel, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
   ++*L.counter;
   // weight gradients: reductions over the batch, queued for one batched launch
   auto add = [&](const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int I, int N) {

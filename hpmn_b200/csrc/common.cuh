@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/hpmn_b200.h"
@@ -270,6 +271,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor in the stream is
+// still running (as soon as every CTA of the predecessor has executed pdl_trigger() or exited); it must call pdl_wait()
+// before it touches anything the predecessor writes.  Used to hide the prologue of the wavefront kernels (weights ->
+// registers / shared memory, barrier setup) behind the tail of the GEMM / attention kernel in front of them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -289,6 +297,21 @@ struct Launch {   // launch bookkeeping shared with the ctx
   int64_t* counter;
   int sms;
 };
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute (HPMN_NO_PDL=1: plain launch)
+template <class... Params, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool off = [] { const char* e = getenv("HPMN_NO_PDL"); return e && e[0] == '1'; }();
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
+}
+#endif
 
 void launch_gather_fwd(const Launch&, const Dims&, bool mask_id0, int front_pad, int64_t V, const int32_t* ids,
                        const float* table, float* x, float* iderr, cudaStream_t st);

@@ -32,6 +32,8 @@ constexpr int F2_KL = (FC1 + F2_KS - 1) / F2_KS;
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const __grid_constant__ HeadArgs a) {
   __shared__ float sBn[MR], sAct1[FC1], sAct2[FC2], sPart[F2_KS][FC2];
+  pdl_trigger();
+  pdl_wait();                                           // launched early (launch_pdl): the kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, R = a.R;
   const float* __restrict__ P = a.params;
   const bool drop = a.keep_prob < 1.f;
@@ -112,6 +114,8 @@ head_bwd_kernel(const __grid_constant__ HeadArgs a) {
   __shared__ __align__(16) float sDl1[FC1];
   __shared__ __align__(16) float sDl2[FC2];
   __shared__ float sDlogit, sPart[2][MR];
+  pdl_trigger();
+  pdl_wait();                                           // launched early (launch_pdl): the kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, R = a.R;
   const float* __restrict__ P = a.params;
   const bool drop = a.keep_prob < 1.f;
@@ -203,7 +207,7 @@ void launch_head_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, cons
                      const HeadWs& ws, cudaStream_t st) {
   HeadArgs a = make_args(d, pl, hy, row0, repre, labels, params, ws);
   a.pred = pred; a.logit = logit; a.scalars = scalars;
-  head_fwd_kernel<<<d.B, 256, 0, st>>>(a);
+  launch_pdl(head_fwd_kernel, dim3(d.B), dim3(256), (size_t)0, st, a);
   ++*L.counter;
 }
 
@@ -212,7 +216,7 @@ void launch_head_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, cons
                      const HeadWs& ws, AtbBatch& batch, cudaStream_t st) {
   HeadArgs a = make_args(d, pl, hy, row0, repre, labels, params, ws);
   a.pred_in = pred; a.drepre = drepre;
-  head_bwd_kernel<<<d.B, 256, 0, st>>>(a);
+  launch_pdl(head_bwd_kernel, dim3(d.B), dim3(256), (size_t)0, st, a);
   ++*L.counter;
   auto add = [&](const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int I, int N) {
     if (batch.n == ATB_MAX) { launch_atb_batch(L, batch, st); batch.n = 0; batch.blocks = 0; }

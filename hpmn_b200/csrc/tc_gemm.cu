@@ -92,6 +92,7 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
   constexpr int SROW = NH + 4;                    // staging row stride (floats): an odd number of float4s
   static_assert(NH % 16 == 0 && ((SROW / 4) & 1) == 1, "epilogue pass width");
   static_assert(128 * SROW * 4 <= 2 * KC * CHS_A, "staging must fit in the operand buffer");
+  pdl_trigger();                                  // a dependent wavefront kernel may set itself up while this grid drains
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sAhi = smem_raw;
   unsigned char* sAlo = sAhi + KC * CHS_A;

@@ -130,18 +130,22 @@ __device__ __forceinline__ float half_finish(float mine, float other) { return m
 // warp ids.  Roles are spread so that the estimated load per sub-partition is balanced and the critical layer-0 warps
 // share theirs only with the lightest roles; inside a sub-partition the heaviest role gets the highest warp id.
 struct WarpPlan { int n; signed char layer[16], sample[16], helper[16]; };
-static WarpPlan plan_warps(int L, int nspc, bool with_helper) {
+static WarpPlan plan_warps(int L, int nspc, bool with_helper, const char* env_weights = nullptr) {
   struct Role { int layer, sample, helper; double w; };
   Role roles[16]; int nr = 0;
+  // experiment hook: HPMN_WAVE_WF / HPMN_WAVE_WB = "w0,w1,w2,w3,w4,whelper" override the per-layer load estimates
+  double ow[6] = {-1, -1, -1, -1, -1, -1};
+  if (const char* e = env_weights ? getenv(env_weights) : nullptr) sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", ow, ow + 1, ow + 2, ow + 3, ow + 4, ow + 5);
   for (int s = 0; s < nspc; ++s)
     for (int k = 0; k < L; ++k) {
       double w = k == 0 ? 2.0 : 1.0;                     // layer 0 is the critical path: keep its sub-partition quiet
       for (int q = 0; q < k; ++q) w *= 0.5;              // layer k runs ~2^-k of layer 0's steps ...
       if (k >= 1) w *= (with_helper && k == 1) ? 1.1 : 1.9;   // ... each ~2x as expensive unless a helper takes the matvec
+      if (k < 5 && ow[k] >= 0) w = ow[k];
       roles[nr++] = Role{k, s, 0, w};
     }
   if (with_helper && L > 1)
-    for (int s = 0; s < nspc; ++s) roles[nr++] = Role{1, s, 1, 0.45};
+    for (int s = 0; s < nspc; ++s) roles[nr++] = Role{1, s, 1, ow[5] >= 0 ? ow[5] : 0.45};
   for (int a = 0; a < nr; ++a)                            // heaviest first
     for (int b = a + 1; b < nr; ++b)
       if (roles[b].w > roles[a].w) { Role t = roles[a]; roles[a] = roles[b]; roles[b] = t; }
@@ -612,6 +616,8 @@ wave_fwd_kernel(const __grid_constant__ WaveArgs a) {
     }
   fence_mbar_init();
   __syncthreads();
+  pdl_trigger();                                         // the attention / dX kernel behind may be scheduled as SMs free up
+  pdl_wait();                                            // everything above only read weights written two launches ago
   if (b >= a.B || k < 0) return;                         // ragged last CTA: the whole warp leaves together
 
   if (helper) {                                          // layer 1's projection warp
@@ -669,9 +675,9 @@ bool launch_wave_fwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   for (int k = 0; k < d.L; ++k) { a.st[k] = st[k]; a.Wh[k] = pk.Wh[k]; a.Wx[k] = pk.Wx[k]; a.bx[k] = pk.bx[k]; a.S[k] = d.S[k]; a.P[k] = d.P[k]; }
   cudaFuncSetAttribute(wave_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
   const int grid = (d.B + nspc - 1) / nspc;
-  const WarpPlan wp = plan_warps(d.L, nspc, d.L > 1);
+  const WarpPlan wp = plan_warps(d.L, nspc, d.L > 1, "HPMN_WAVE_WF");
   for (int i = 0; i < 16; ++i) { a.wlayer[i] = wp.layer[i]; a.wsample[i] = wp.sample[i]; a.whelper[i] = wp.helper[i]; }
-  wave_fwd_kernel<<<grid, 32 * wp.n, sm.total, st_>>>(a);
+  launch_pdl(wave_fwd_kernel, dim3(grid), dim3(32 * wp.n), (size_t)sm.total, st_, a);   // prologue overlaps the projection GEMM's tail
   { cudaError_t e = cudaGetLastError();                  // resources: the caller falls back to the per-layer kernels
     if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_fwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * wp.n, sm.total); return false; } }
   ++*L.counter;
@@ -1152,6 +1158,8 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     }
   fence_mbar_init();
   __syncthreads();
+  pdl_trigger();                                         // the attention / dX kernel behind may be scheduled as SMs free up
+  pdl_wait();                                            // everything above only read weights written two launches ago
   if (b >= a.B || k < 0) return;
 
   Handoff* hin = k < L - 1 ? &hand[k * nspc + si] : nullptr;        // from layer k+1
@@ -1192,16 +1200,16 @@ bool launch_wave_bwd(const Launch& L, const Dims& d, const PackLayout& pk, const
   a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
   for (int k = 0; k < d.L; ++k) { a.st[k] = st[k]; a.da[k] = da[k]; a.WhT[k] = pk.WhT[k]; a.WxT[k] = pk.WxT[k]; a.S[k] = d.S[k]; a.P[k] = d.P[k]; }
   const int grid = (d.B + nspc - 1) / nspc;
-  const WarpPlan wp = plan_warps(d.L, nspc, d.L > 1);
+  const WarpPlan wp = plan_warps(d.L, nspc, d.L > 1, "HPMN_WAVE_WB");
   for (int i = 0; i < 16; ++i) { a.wlayer[i] = wp.layer[i]; a.wsample[i] = wp.sample[i]; a.whelper[i] = wp.helper[i]; }
   bool debug = false;
   { static int once = 0; const char* e = getenv("HPMN_WAVE_DEBUG"); debug = e && e[0] == '1' && once++ == 3; }   // 4th call only
   if (debug) {
     cudaFuncSetAttribute(wave_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    wave_bwd_kernel<true><<<grid, 32 * wp.n, sm.total, st_>>>(a);
+    launch_pdl(wave_bwd_kernel<true>, dim3(grid), dim3(32 * wp.n), (size_t)sm.total, st_, a);
   } else {
     cudaFuncSetAttribute(wave_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    wave_bwd_kernel<false><<<grid, 32 * wp.n, sm.total, st_>>>(a);
+    launch_pdl(wave_bwd_kernel<false>, dim3(grid), dim3(32 * wp.n), (size_t)sm.total, st_, a);   // ... the attention backward's tail
   }
   { cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_bwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * wp.n, sm.total); return false; } }
