@@ -162,10 +162,16 @@ def run_product(args, cfg_name, cfg):
     d_lab = [t.to(dev) for t in h_lab]
     loss_batch = B * world
 
+    if world > 1 and os.environ.get("HPMN_COMM_OVERLAP") == "1":
+        # experiment (off by default): start the table-gradient all-reduce as soon as the scatter is done, beside the GRU
+        # weight-gradient reduction.  Measured at N=2: 1.3227 vs 1.3253 ms -- the second collective and the contention with the
+        # weight-gradient kernel eat the ~110 us head start (profiles/r1_v8_wave_step_timeline.md, section 5)
+        eng.set_comm_stream(torch.cuda.Stream(device=dev))
+
     def step_dev(i):
         eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=args.keep_prob, seed=i, loss_batch=loss_batch)
         if world > 1:
-            hd.allreduce_flat(eng.flat_grad)          # the step's single collective
+            hd.allreduce_grads(eng)                   # the step's single collective (flat [dense | table] buffer)
 
     def step_host(i):
         # the feed of step i+1 is staged on the library's copy stream while step i computes (double-buffered H2D); every
@@ -174,7 +180,7 @@ def run_product(args, cfg_name, cfg):
             eng.prefetch_host(h_ids[0], h_lab[0], B)
         eng.step_host_pinned(True, args.keep_prob, i, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB], prefetch_next=(h_ids[(i + 1) % NB], h_lab[(i + 1) % NB]))
         if world > 1:
-            hd.allreduce_flat(eng.flat_grad)
+            hd.allreduce_grads(eng)
 
     def timed(fn, steps):
         hd.barrier(); torch.cuda.synchronize(dev)

@@ -51,6 +51,7 @@ SYMBOLS = {
     "hpmn_destroy": (None, [_P]),
     "hpmn_last_error": (C.c_char_p, [_P]),
     "hpmn_launch_count": (_L, [_P]),
+    "hpmn_set_comm_stream": (_I, [_P, _P]),
     "hpmn_param_tensors": (_I, [_SH]),
     "hpmn_param_count": (_L, [_SH]),
     "hpmn_param_offsets": (_I, [_SH, C.POINTER(_L), C.POINTER(_L), _I]),

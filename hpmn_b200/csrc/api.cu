@@ -7,6 +7,8 @@
 
 #include <vector>
 
+#include <functional>
+
 #include "common.cuh"
 
 using namespace hpmn;
@@ -25,6 +27,8 @@ struct hpmn_ctx {
   // side stream: weight-gradient reductions run here, concurrently with the latency-bound recurrent chain on the
   // caller's stream (forked / joined with events, so the caller still sees plain stream order)
   cudaStream_t side;
+  cudaStream_t comm;        // caller's collective stream (hpmn_set_comm_stream): told when the table gradient is final
+  cudaEvent_t ev_dtable;
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
@@ -213,8 +217,11 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
 
 // memory backward: top layer first; da overwrites the projections.  The recurrent chain (rec_bwd -> dx GEMM -> next
 // layer) stays on `st`; each layer's weight-gradient reduction only needs that layer's da and is forked to the side stream.
+// after_dx (optional) is called once dX of layer 0 is queued on `st`: the caller's scatter then goes in FRONT of the weight-
+// gradient kernel (launch order = dispatch order), so the table gradient is final ~60 us after the recurrence instead of
+// ~175 us and a table all-reduce on another stream (hpmn_set_comm_stream) runs beside the weight-gradient reduction.
 static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const float* dmemory, float* dx0, float* grads,
-                           bool ov, cudaStream_t st, bool join = true) {
+                           bool ov, cudaStream_t st, bool join = true, const std::function<void()>& after_dx = nullptr) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   float* pw = p.f(p.wl.pw);
@@ -229,6 +236,9 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
     if (done) {
       cudaStream_t ws = st;
       if (ov) { cudaEventRecord(ctx->ev_fork[0], st); cudaStreamWaitEvent(ctx->side, ctx->ev_fork[0], 0); ws = ctx->side; }
+      { Bracket b(ctx, st, HPMN_K_DX);
+        dense_gemm(ctx, L, dap[0], G3, pw + p.pk.WxT[0], nullptr, dx0, (int64_t)d.B * d.S[0], d.DinP[0], G3, st); }
+      if (after_dx) after_dx();
       { Bracket b(ctx, st, HPMN_K_WGRAD);
         const float* xa[HPMN_MAX_LAYERS]; int64_t lx[HPMN_MAX_LAYERS];
         float *gWg[HPMN_MAX_LAYERS], *gbg[HPMN_MAX_LAYERS], *gWc[HPMN_MAX_LAYERS], *gbc[HPMN_MAX_LAYERS];
@@ -241,8 +251,6 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
           for (int k = 0; k < d.L; ++k)
             launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], ws);
       }
-      { Bracket b(ctx, st, HPMN_K_DX);
-        dense_gemm(ctx, L, dap[0], G3, pw + p.pk.WxT[0], nullptr, dx0, (int64_t)d.B * d.S[0], d.DinP[0], G3, st); }
       if (ov && join) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }
       return;
     }
@@ -265,6 +273,7 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
     { Bracket b(ctx, st, HPMN_K_DX);
       dense_gemm(ctx, L, da, G3, pw + p.pk.WxT[k], nullptr, dxk, (int64_t)d.B * d.S[k], d.DinP[k], G3, st); }
   }
+  if (after_dx) after_dx();
   if (ov && join) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }
 }
 
@@ -310,6 +319,8 @@ int hpmn_create(hpmn_ctx** out, int device) {
   for (auto& ev : ctx->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_zero, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_dtable, cudaEventDisableTiming);
+  ctx->comm = nullptr;
   ctx->zero_pending = false;
   cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
@@ -332,6 +343,7 @@ void hpmn_destroy(hpmn_ctx* ctx) {
   for (auto& ev : ctx->ev_fork) cudaEventDestroy(ev);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_zero);
+  cudaEventDestroy(ctx->ev_dtable);
   cudaEventDestroy(ctx->ev_copy); for (auto& ev : ctx->ev_consumed) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->copy);
   cudaStreamDestroy(ctx->side);
@@ -344,6 +356,12 @@ void hpmn_destroy(hpmn_ctx* ctx) {
 
 const char* hpmn_last_error(hpmn_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 int64_t hpmn_launch_count(hpmn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hpmn_set_comm_stream(hpmn_ctx* ctx, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  ctx->comm = (cudaStream_t)stream;
+  return HPMN_OK;
+}
 
 int hpmn_param_tensors(const hpmn_shape* s) {
   Dims d = make_dims(s);
@@ -544,11 +562,17 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
     } }
   // the weight-gradient reductions on the side stream are joined behind the scatter: the dX GEMM and the scatter (61 us)
   // run beside the 114 us weight-gradient kernel instead of in front of / behind it
-  run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), p.f(p.wl.dxk[0]), grads, ov, st, false);
-  if (ctx->zero_pending) { cudaStreamWaitEvent(st, ctx->ev_zero, 0); ctx->zero_pending = false; }
-  { Bracket b(ctx, st, HPMN_K_SCATTER);
-    launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids + (int64_t)r0 * d.T * d.F,
-                      p.f(p.wl.dxk[0]), p.f(p.wl.dlast), dtable, st); }
+  auto scatter = [&]() {
+    if (ctx->zero_pending) { cudaStreamWaitEvent(st, ctx->ev_zero, 0); ctx->zero_pending = false; }
+    { Bracket b(ctx, st, HPMN_K_SCATTER);
+      launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids + (int64_t)r0 * d.T * d.F,
+                        p.f(p.wl.dxk[0]), p.f(p.wl.dlast), dtable, st); }
+    if (side_ok && ctx->comm) {                          // whole-batch step: the table gradient is final from here on
+      cudaEventRecord(ctx->ev_dtable, st);
+      cudaStreamWaitEvent(ctx->comm, ctx->ev_dtable, 0);
+    }
+  };
+  run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), p.f(p.wl.dxk[0]), grads, ov, st, false, scatter);
   if (ov) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }
 }
 

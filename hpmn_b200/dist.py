@@ -47,6 +47,24 @@ def allreduce_flat(flat_grad: torch.Tensor) -> torch.Tensor:
     return flat_grad
 
 
+def allreduce_grads(eng) -> None:
+    """The step's collectives for an HpmnEngine whose comm stream is set (eng.set_comm_stream): ONE all-reduce of the
+    embedding-table gradient (212 MB at XLong) on the comm stream -- the library made that stream wait for the scatter, which
+    is queued in front of the GRU weight-gradient reduction, so the transfer runs beside the rest of the backward pass -- and
+    one of the 0.4 MB dense block on the caller's stream once the call has finished.  Both are complete for the caller's
+    stream on return.  Without a comm stream this is allreduce_flat(eng.flat_grad)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    comm = getattr(eng, "comm_stream", None)
+    if comm is None:
+        dist.all_reduce(eng.flat_grad, op=dist.ReduceOp.SUM)
+        return
+    with torch.cuda.stream(comm):
+        dist.all_reduce(eng.dtable, op=dist.ReduceOp.SUM)
+    dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
+    torch.cuda.current_stream(eng.device).wait_stream(comm)
+
+
 def allreduce_scalars(scalars: torch.Tensor) -> torch.Tensor:
     """logloss (already divided by the global batch), covreg and loss are sums over ranks."""
     if dist.is_initialized() and dist.get_world_size() > 1:

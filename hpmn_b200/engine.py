@@ -47,6 +47,7 @@ class HpmnEngine:
         self.table_off = (self.n_params + 63) & ~63
         self.flat = torch.zeros(self.table_off + self.n_table, **f32)
         self.flat_grad = torch.zeros_like(self.flat)
+        self.comm_stream = None
         self.params = self.flat[: self.n_params]
         self.table = self.flat[self.table_off:].view(shape.V, shape.E)
         self.grads = self.flat_grad[: self.n_params]
@@ -140,6 +141,13 @@ class HpmnEngine:
         c = self.shape.to_c()
         c.B = B
         return c
+
+    def set_comm_stream(self, stream: Optional["torch.cuda.Stream"]):
+        """Multi-GPU overlap: `stream` waits, inside every backward call, for the point where the table gradient is final
+        (hpmn_set_comm_stream); hpmn_b200.dist.allreduce_grads() all-reduces `dtable` on it beside the rest of the backward
+        pass.  None clears the hook."""
+        self.comm_stream = stream
+        _lib.check(self.lib.hpmn_set_comm_stream(self.ctx, C.c_void_p(stream.cuda_stream if stream is not None else None)), self.ctx)
 
     def forward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0, loss_batch: int = 0):
         """ids [B,T,F] int32 cuda, labels [B] int32 cuda; results land in self.pred / logit / w_hop0 / scalars."""

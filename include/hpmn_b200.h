@@ -78,6 +78,12 @@ void hpmn_destroy(hpmn_ctx* ctx);
 const char* hpmn_last_error(hpmn_ctx* ctx); /* ctx may be NULL: last error of a failed hpmn_create */
 /* number of kernels this ctx has launched since create (bench.py's gpu_launches) */
 int64_t hpmn_launch_count(hpmn_ctx* ctx);
+/* Multi-GPU overlap hook (the reference has no distributed code; replaces nothing).  `stream` (a cudaStream_t, or NULL to
+ * clear) is made to wait, inside every hpmn_forward_backward / hpmn_step_host call, for the point at which the embedding-table
+ * gradient `dtable` is final -- the scatter is queued in front of the GRU weight-gradient reduction -- so the caller's
+ * all-reduce of `dtable` on that stream runs beside the rest of the backward pass.  The dense gradients are final when the
+ * call's own stream reaches the end of the call, as before. */
+int hpmn_set_comm_stream(hpmn_ctx* ctx, void* stream);
 
 /* ---- layouts (pure host functions, usable without a GPU) ---------------------------------- */
 /* Dense parameters live in ONE flat fp32 buffer (gradients in a twin buffer of the same layout):
