@@ -402,3 +402,32 @@ def test_two_gpu_gradient_equals_single():
     tot = parts[0] + parts[1]
     ref = full.flat_grad.cpu()
     assert float((tot - ref).norm() / ref.norm()) < 1e-5
+
+
+def test_comm_stream_sees_final_table_gradient():
+    """hpmn_set_comm_stream: a stream handed to the library waits, inside the backward call, for the scatter -- work queued
+    on it right after the call (the table all-reduce of hpmn_b200.dist.allreduce_grads) must see the final dtable even though
+    the call's own stream is still busy with the GRU weight-gradient reduction."""
+    import torch
+    from hpmn_b200.engine import HpmnEngine
+    sh = HpmnShape(B=64, T=200, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=5000)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    ids, labels = O.synthetic_batch(osh)
+    eng = HpmnEngine(sh, device=0, memory_reg=1e-3, table=table, params=params)
+    d_ids, d_lab = torch.as_tensor(ids, device="cuda:0"), torch.as_tensor(labels, device="cuda:0")
+    eng.forward_backward(d_ids, d_lab)
+    torch.cuda.synchronize()
+    ref = eng.dtable.clone()
+    comm = torch.cuda.Stream(device=eng.device)
+    eng.set_comm_stream(comm)
+    for _ in range(3):
+        eng.forward_backward(d_ids, d_lab)
+        with torch.cuda.stream(comm):
+            snap = eng.dtable.clone()            # ordered behind the library's "dtable final" event only
+        torch.cuda.current_stream().wait_stream(comm)
+        torch.cuda.synchronize()
+        assert torch.equal(snap, eng.dtable)
+        assert float((snap - ref).norm() / ref.norm()) < 1e-5     # atomics: summation order differs between runs
+    eng.set_comm_stream(None)
+    eng.close()
