@@ -54,6 +54,15 @@ constexpr int BLK = 8;        // steps per block of the latency-critical loops =
 // registers for batching their other shared-memory weight loads.  Measured (XLong, B=256): forward 0.294 -> 0.292 ms; backward
 // 0.266 -> 0.290 ms (layer 2's step gets 30 % shorter, but the extra LSU traffic slows the co-critical layers 0 and 1) => off.
 constexpr bool CS_FWD = HPMN_CSMEM_FWD != 0, CS_BWD = HPMN_CSMEM_BWD != 0;
+// Experimental: backward kernel with ONE warp per sample for all layers >= 2 (8 warps per CTA -> 255 registers per thread
+// instead of 168), see wave_bwd_upper.  Parity-green (GPU test suite), but slower so far: rec_bwd 0.365 ms against 0.265 ms for
+// one warp per layer (XLong, B=256).  Its arithmetic is fast (820 cycles per step against ~1400), the warp loses ~900 cycles
+// per step outside it -- a first cut with two step variants in the loop (13 KB of SASS) ran at 0.408 ms, so instruction
+// fetch is the suspect.  Off by default; -DHPMN_BWD_UPPER=1 builds it, HPMN_NO_BWD_UPPER=1 switches it off at run time.
+#ifndef HPMN_BWD_UPPER
+#define HPMN_BWD_UPPER 0
+#endif
+constexpr bool BWD_UPPER = HPMN_BWD_UPPER != 0;
 constexpr int FUNR = HPMN_FUNR, BUNR = HPMN_BUNR, GUNR = HPMN_GUNR;   // GUNR: the loops of the layers off the critical path
 constexpr int WAVE_MAX_L = 10;
 
@@ -709,15 +718,19 @@ struct WaveBwdArgs {
 };
 
 __host__ __device__ constexpr int bwd_region_bytes(int ch, int ns) {
-  return ns * (ch + 1) * ST * 4 + 2 * ch * G3 * 4 + 3 * 128 + 128;   // state ring | da ring | sh_c,sh_r,sh_u | mbarriers
+  return ns * (ch + 1) * ST * 4 + 2 * ch * G3 * 4 + 3 * 128 + 128 + 128;   // state ring | da ring | sh_c,sh_r,sh_u | mbarriers | dh (upper warp)
 }
 
 struct WaveBwdSmem {
   int wxt, whc, hand, hand3, l0, l1, l2, lk, total;
-  __host__ __device__ WaveBwdSmem(int L, int nspc) {
+  int wxt_first;                   // first layer whose W_x^T is kept in shared memory
+  __host__ __device__ WaveBwdSmem(int L, int nspc, bool up) {
     int off = 0;
-    wxt = off; off += (L - 1) * 3 * 8 * HP * 16;           // float4 [g][q][lane] = (mine pair | other pair) per layer >= 1
-    whc = off; off += (L > 2 ? L - 2 : 0) * 8 * HP * 16;   // candidate-gate W_h^T of layers >= 2, float4 [q][lane]
+    wxt_first = up ? 2 : 1;        // upper-warp mode: the helper reads layer 1's W_x^T straight from global memory
+    wxt = off; off += (L > wxt_first ? L - wxt_first : 0) * 3 * 8 * HP * 16;   // float4 [g][q][lane] = (mine pair | other pair)
+    whc = off;
+    if (up) off += (L > 2 ? L - 2 : 0) * 3 * 8 * HP * 16;  // W_h^T (all gates) of layers >= 2, float4 [g][q][lane]
+    else off += (CS_BWD && L > 2 ? L - 2 : 0) * 8 * HP * 16;   // candidate-gate W_h^T of layers >= 2, float4 [q][lane]
     off = (off + 127) & ~127;
     hand = off; off += (L - 1) * nspc * (int)sizeof(Handoff);
     off = (off + 127) & ~127;
@@ -725,8 +738,8 @@ struct WaveBwdSmem {
     off = (off + 127) & ~127;
     l0 = off; off += nspc * bwd_region_bytes(BCH0, BNS0);
     l1 = off; off += (L > 1 ? nspc : 0) * bwd_region_bytes(BCH0, BNS0);   // layer 1 runs the same loop as layer 0
-    l2 = off; off += (L > 2 ? nspc : 0) * bwd_region_bytes(BCH2, BNSK);        // layer 2: next in line for the critical path
-    lk = off; off += (L > 3 ? L - 3 : 0) * nspc * bwd_region_bytes(BCHK, BNSK);
+    l2 = off; off += (!up && L > 2 ? nspc : 0) * bwd_region_bytes(BCH2, BNSK); // layer 2: next in line for the critical path
+    lk = off; off += (up ? (L > 2 ? L - 2 : 0) : (L > 3 ? L - 3 : 0)) * nspc * bwd_region_bytes(BCHK, BNSK);
     total = off;
   }
 };
@@ -747,7 +760,8 @@ __device__ __forceinline__ void load_bwd_weights(BwdW& w, const float* WhT /*[3]
 // gradient handed down to the layer below, dx = da W_x^T, is accumulated from the same broadcast halves as they arrive
 // (W_x^T from shared memory, [g][q][mine|other][lane]) -- nothing but six accumulators stays live for it.
 // The caller closes the step with __syncwarp().
-template <bool WITH_DX>
+// ALL_SMEM (layers >= 3 of the upper warp): all three recurrent matrices come from shared memory (myWhT: [g][q][lane]).
+template <bool WITH_DX, bool ALL_SMEM = false>
 __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, bool first_step, float dh, float add, int i,
                                               float* sh_c, float* sh_r, float* sh_u, float* orow, float& dar, float& dau,
                                               float& dac, const float4* myWxT, const float4* myWhcT, float& dx) {
@@ -782,7 +796,10 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
   float2 xm0 = make_float2(0.f, 0.f), xo0 = xm0, xm1 = xm0, xo1 = xm0, xm2 = xm0, xo2 = xm0;
   float2 cm = xm0, co = xm0;
   float drh;
-  if (CS_BWD) {
+  if (ALL_SMEM) {
+    half_part_smem(v, myWhcT + (2 * 8) * HP + i, HP, cm, co);
+    drh = half_finish(cm.x + cm.y, co.x + co.y);
+  } else if (CS_BWD) {
     half_part_smem(v, myWhcT + i, HP, cm, co);           // candidate-gate W_h^T from shared memory (see gru_fwd_step, C_SMEM)
     drh = half_finish(cm.x + cm.y, co.x + co.y);
   } else {
@@ -794,10 +811,23 @@ __device__ __forceinline__ float gru_bwd_step(const BwdW& w, const float* row, b
   __syncwarp();
   half_part_smem(v, myWxT + (2 * 8) * HP + i, HP, xm2, xo2);                    // rows 64..95 of W_x^T: da_c
   load_vec_half(v, sh_u, i);
-  const Part pu = half_part(v, w.u, fmaf(dh, u, add));
+  Part pu, pr;
+  if (ALL_SMEM) {
+    float2 m = make_float2(fmaf(dh, u, add), 0.f), o = make_float2(0.f, 0.f);
+    half_part_smem(v, myWhcT + (1 * 8) * HP + i, HP, m, o);
+    pu.m = m.x + m.y; pu.o = o.x + o.y;
+  } else {
+    pu = half_part(v, w.u, fmaf(dh, u, add));
+  }
   half_part_smem(v, myWxT + (1 * 8) * HP + i, HP, xm1, xo1);                    // rows 32..63: da_u
   load_vec_half(v, sh_r, i);
-  const Part pr = half_part(v, w.r, drh * r);
+  if (ALL_SMEM) {
+    float2 m = make_float2(drh * r, 0.f), o = make_float2(0.f, 0.f);
+    half_part_smem(v, myWhcT + (0 * 8) * HP + i, HP, m, o);
+    pr.m = m.x + m.y; pr.o = o.x + o.y;
+  } else {
+    pr = half_part(v, w.r, drh * r);
+  }
   half_part_smem(v, myWxT + (0 * 8) * HP + i, HP, xm0, xo0);                    // rows 0..31: da_r
   orow[0] = dar; orow[HP] = dau; orow[2 * HP] = dac;
   const float dhn = half_finish(pr.m + pu.m, pr.o + pu.o);
@@ -956,10 +986,15 @@ __device__ __forceinline__ void wave_bwd_dx_helper(const WaveBwdArgs& a, int i, 
     }
   };
   HalfW w[3];                                            // gate g: rows g*32 .. g*32+31 of W_x^T
+  if (myWxT != nullptr) {
 #pragma unroll
-  for (int g = 0; g < 3; ++g)
+    for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { const float4 t = myWxT[(g * 8 + q) * HP + i]; w[g].m[q] = make_float2(t.x, t.y); w[g].o[q] = make_float2(t.z, t.w); }
+      for (int q = 0; q < 8; ++q) { const float4 t = myWxT[(g * 8 + q) * HP + i]; w[g].m[q] = make_float2(t.x, t.y); w[g].o[q] = make_float2(t.z, t.w); }
+  } else {                                               // upper-warp mode: layer 1's W_x^T is not staged in shared memory
+#pragma unroll
+    for (int g = 0; g < 3; ++g) load_half(w[g], a.pw + a.WxT[1] + g * HP * HP, i, 1.f);   // rows g*32.. of [96][32] = [32 in][32 out]
+  }
   const unsigned n = (unsigned)a.S[1], vofs = group_vofs(a.S[0]);
   for (unsigned idx = 0; idx < n; ++idx) {
     const int slot = idx & (HRS - 1), gi = (idx / HG) & 1;
@@ -1115,23 +1150,159 @@ __device__ __forceinline__ void wave_bwd_layer(const WaveBwdArgs& a, int k, int 
            clock64() - t_start, (clock64() - t_start) / S, w_in, w_out, w_tma, q_hin, q_step, q_out);
 }
 
-// Registers are partitioned per SM sub-partition (16 K each): 12 warps = 3 per SMSP = at most 168 per thread.
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Upper warp (backward): ONE warp per sample walks layers 2 .. L-1.  With one warp per layer the CTA had 12 warps, i.e. 168
+// registers per thread, and the layers >= 2 -- 96 registers of recurrent weights plus a 96 x 32 mat-vec with W_x^T from
+// shared memory -- could keep only a handful of weight loads in flight: ~1400 cycles per step, which made layer 2 the
+// slowest link of the whole backward pipeline (profiles/r1_v10_wave_ncu.md).  Together these layers fire 0.44 times per
+// layer-0 step, so one warp has the time; 8 warps per CTA lift the cap to 255 registers, and the hand-offs between the
+// layers >= 2 need no barriers any more (the dx of layer k+1 is simply a register of the same lane).
+// For every step of layer 2 (reverse time) the layers above that fired at that step are processed first, top down
+// (hpmn.py:124-128 in reverse).  Layer 2 keeps its W_h^T in registers, layers >= 3 read all weights from shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
 template <bool DBG>
-__global__ void __launch_bounds__(384)
+__device__ __forceinline__ void wave_bwd_upper(const WaveBwdArgs& a, int b, int i, unsigned char* dsm, const WaveBwdSmem& sm,
+                                               int si, Handoff* hout, const float4* sWxT, const float4* sWhT3) {
+  constexpr int NS = BNSK;
+  const int L = a.L, nspc = a.nspc, H = a.H;
+  const bool dbg = DBG && blockIdx.x == 0;
+  const long long t_start = DBG ? clock64() : 0;
+  long long w_out = 0, w_tma = 0, q_step = 0;
+  BwdW w2;                                               // unused: every layer of this warp reads its weights from shared memory
+
+  // per-layer bookkeeping lives in the layer's shared-memory block (no runtime-indexed register arrays, no integer divisions:
+  // the first cut of this loop spent 1400 cycles per step on `/` and `%`): st[0] = next step to process, st[1] = steps until
+  // the next firing step (0 = this one fired)
+  struct Lay { float* s_st; float* s_da; float* sh_c; float* sh_r; float* sh_u; uint64_t* full; float* sh_dh; int* st; int CH, chs; };
+  auto layer = [&](int k) {
+    Lay l;
+    l.chs = 2;
+    static_assert(BCHK == 4, "chunk size is a power of two (shifts below)");
+    l.CH = 1 << l.chs;
+    unsigned char* reg = dsm + sm.lk + ((k - 2) * nspc + si) * bwd_region_bytes(BCHK, BNSK);
+    l.s_st = reinterpret_cast<float*>(reg);
+    l.s_da = l.s_st + NS * (l.CH + 1) * ST;
+    l.sh_c = l.s_da + 2 * l.CH * G3;
+    l.sh_r = l.sh_c + 32;
+    l.sh_u = l.sh_r + 32;
+    l.full = reinterpret_cast<uint64_t*>(l.sh_u + 32);
+    l.st = reinterpret_cast<int*>(l.full + 8);
+    l.sh_dh = l.sh_u + 64;
+    return l;
+  };
+  auto issue = [&](int k, const Lay& l, int ci, int stage) {   // lane 0: state rows s0-1 .. s0+len-1 of chunk ci of layer k
+    const int S = a.S[k], s0 = ci * l.CH, len = min(l.CH, S - s0);
+    const float* sb = a.st[k] + (int64_t)b * S * ST;
+    const uint32_t rows = (uint32_t)(s0 > 0 ? len + 1 : len);
+    mbar_expect_tx(&l.full[stage], rows * ST * 4);
+    if (s0 > 0) bulk_g2s(l.s_st + stage * (l.CH + 1) * ST, sb + (int64_t)(s0 - 1) * ST, rows * ST * 4, &l.full[stage]);
+    else bulk_g2s(l.s_st + stage * (l.CH + 1) * ST + ST, sb, rows * ST * 4, &l.full[stage]);
+  };
+  for (int k = 2; k < L; ++k) {
+    const Lay l = layer(k);
+    if (i == 0) { for (int q = 0; q < NS; ++q) mbar_init(&l.full[q], 1); l.st[0] = a.S[k] - 1; l.st[1] = 0; }
+    l.sh_dh[i] = i < H ? __ldg(a.dmemory + ((int64_t)b * L + k) * H + i) : 0.f;   // memory-slot gradient enters at the last step
+  }
+  if (i == 0) fence_mbar_init();
+  __syncwarp();
+  if (i == 0)
+    for (int k = 2; k < L; ++k) {
+      const Lay l = layer(k);
+      const int nch = (a.S[k] + l.CH - 1) >> l.chs;
+      for (int it = 0; it < NS && it < nch; ++it) issue(k, l, nch - 1 - it, it);
+    }
+  __syncwarp();
+
+  // one reverse step of layer k at its step s; dx_in = gradient handed down by layer k+1 (0 if step s did not fire); returns the
+  // dx for layer k-1
+  auto step = [&](int k, const Lay& l, int s, float dx_in) -> float {
+    const int S = a.S[k], CH = l.CH, nch = (S + CH - 1) >> l.chs;
+    const int ci = s >> l.chs, t = s & (CH - 1), it = nch - 1 - ci, stage = it % NS, s0 = ci << l.chs, len = min(CH, S - s0);
+    if (t == len - 1) {                                  // first step of this chunk (reverse order)
+      mbar_wait_t(&l.full[stage], (uint32_t)(it / NS) & 1u, w_tma, dbg);
+      if (it >= 2) {                                     // da buffer it & 1: its store two chunks ago has read its source.  Bulk groups are
+        if (i == k - 2) bulk_wait_read<1>();             // per thread: lane k-2 issues only layer k's stores, so "all but the newest"
+        __syncwarp();                                    // is exactly that store (one lane for all layers blocked ~2 us per chunk)
+      }
+    }
+    const float* row = l.s_st + stage * (CH + 1) * ST + t * ST + i;
+    float* ob = l.s_da + (it & 1) * CH * G3;
+    float* orow = ob + t * G3 + i;
+    const float dh = l.sh_dh[i] + dx_in;
+    float dar, dau, dac, dx;
+    const long long c0 = dbg ? clock64() : 0;
+    float dhn;
+    // ONE copy of the step for every layer (weights from shared memory): with a second, register-weight variant for layer 2
+    // the loop body was ~13 KB of SASS and the warp lost ~900 cycles per step outside the arithmetic
+    dhn = gru_bwd_step<true, true>(w2, row, s == 0, dh, 0.f, i, l.sh_c, l.sh_r, l.sh_u, orow, dar, dau, dac,
+                                   sWxT + (size_t)(k - 2) * 3 * 8 * HP, sWhT3 + (size_t)(k - 2) * 3 * 8 * HP, dx);
+    if (dbg) q_step += clock64() - c0 + (long long)(dx == 12345.f);
+    l.sh_dh[i] = dhn;
+    __syncwarp();                                        // sh_c / sh_r / sh_u free for this layer's next step
+    if (t == 0) {                                        // chunk complete: da rows out, next state chunk in
+      fence_proxy_async();
+      __syncwarp();
+      if (i == k - 2) {
+        bulk_s2g(a.da[k] + ((int64_t)b * S + s0) * G3, ob, (uint32_t)len * G3 * 4);
+        bulk_commit();
+        if (it + NS < nch) issue(k, l, nch - 1 - (it + NS), stage);
+      }
+    }
+    return dx;
+  };
+
+  const int S2 = a.S[2];
+  const unsigned vofs = group_vofs(a.S[1]);
+  unsigned sent = 0;                                     // rows handed to layer 1
+  for (int s2 = S2 - 1; s2 >= 0; --s2) {
+    int top = 2;                                         // layers 3 .. top fired at this step of layer 2
+    while (top + 1 < L && layer(top).st[1] == 0) ++top;
+    float dx = 0.f;
+    for (int k = top; k >= 2; --k) {
+      const Lay l = layer(k);
+      const int sk = l.st[0], rem = l.st[1];
+      dx = step(k, l, sk, dx);                           // (its __syncwarp()s order the bookkeeping reads above before the write below)
+      if (i == 0) { l.st[0] = sk - 1; l.st[1] = rem == 0 ? a.P[k] - 1 : rem - 1; }
+    }
+    __syncwarp();
+    // dx of layer 2 -> layer 1 (wave_bwd_fast): groups of HG rows aligned to ITS chunks
+    const unsigned v = sent + vofs;
+    const int g = (v / HG) & 1;
+    if ((v & (HG - 1)) == 0 && v >= HRS) mbar_wait_t(&hout->gempty[g], (v / HRS - 1) & 1u, w_out, dbg);
+    hout->ring[v & (HRS - 1)][i] = dx;
+    ++sent;
+    if (((v + 1) & (HG - 1)) == 0 || sent == (unsigned)S2) {
+      __syncwarp();
+      if (i == 0) mbar_arrive(&hout->gfull[g]);
+    }
+  }
+  if (i < L - 2) bulk_wait_read<0>();
+  __syncwarp();
+  if (dbg && i == 0 && b == 0)
+    printf("wave_bwd upper warp (layers 2..%d): %d layer-2 steps total %lld cyc (%lld/step)  wait_out %lld  wait_tma %lld  in-steps %lld\n",
+           L - 1, S2, clock64() - t_start, (clock64() - t_start) / S2, w_out, w_tma, q_step);
+}
+
+// Registers are partitioned per SM sub-partition (16 K each): 12 warps = 3 per SMSP = at most 168 per thread; the upper-warp
+// variant (UP) runs 8 warps = 2 per SMSP = 255 per thread.
+template <bool DBG, bool UP>
+__global__ void __launch_bounds__(UP ? 256 : 384)
 wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   const int tid = threadIdx.x, w = tid >> 5, i = tid & 31;
   const int L = a.L, nspc = a.nspc;
   const int k = a.wlayer[w], si = a.wsample[w];         // see plan_warps()
   const int b = blockIdx.x * nspc + si;
-  const WaveBwdSmem sm(L, nspc);
+  const WaveBwdSmem sm(L, nspc, UP);
   float4* sWxT = reinterpret_cast<float4*>(dsm + sm.wxt);
   Handoff* hand = reinterpret_cast<Handoff*>(dsm + sm.hand);
   Handoff3* hand3 = reinterpret_cast<Handoff3*>(dsm + sm.hand3);
 
-  // ---- CTA setup: W_x^T of layers >= 1 in the K-half layout [g][q][lane] x (mine | other) ----
-  for (int e = tid; e < (L - 1) * 3 * 8 * HP; e += blockDim.x) {
-    const int kk = 1 + e / (3 * 8 * HP), r = e % (3 * 8 * HP);
+  // ---- CTA setup: W_x^T of layers >= wxt_first in the K-half layout [g][q][lane] x (mine | other) ----
+  const int nwx = L > sm.wxt_first ? L - sm.wxt_first : 0;
+  for (int e = tid; e < nwx * 3 * 8 * HP; e += blockDim.x) {
+    const int kk = sm.wxt_first + e / (3 * 8 * HP), r = e % (3 * 8 * HP);
     const int g = r / (8 * HP), q = (r / HP) % 8, lane = r % HP;
     const int n = g * HP + 16 * (lane & 1) + 2 * q;
     const float* WxT = a.pw + a.WxT[kk];                 // [96][32]
@@ -1139,12 +1310,23 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
                           __ldg(WxT + n * HP + (lane ^ 1)), __ldg(WxT + (n + 1) * HP + (lane ^ 1)));
   }
   float4* sWhcT = reinterpret_cast<float4*>(dsm + sm.whc);
-  for (int e = tid; e < (L - 2) * 8 * HP; e += blockDim.x) {
-    const int kk = 2 + e / (8 * HP), q = (e / HP) % 8, lane = e % HP;
-    const int n = 16 * (lane & 1) + 2 * q;
-    const float* WcT = a.pw + a.WhT[kk] + 2 * HP * HP;   // [32 j][32 i]
-    sWhcT[e] = make_float4(__ldg(WcT + n * HP + lane), __ldg(WcT + (n + 1) * HP + lane),
-                           __ldg(WcT + n * HP + (lane ^ 1)), __ldg(WcT + (n + 1) * HP + (lane ^ 1)));
+  if (UP) {                                              // W_h^T, all gates, of layers >= 2: [g][q][lane]
+    for (int e = tid; e < (L - 2) * 3 * 8 * HP; e += blockDim.x) {
+      const int kk = 2 + e / (3 * 8 * HP), r = e % (3 * 8 * HP);
+      const int g = r / (8 * HP), q = (r / HP) % 8, lane = r % HP;
+      const int n = 16 * (lane & 1) + 2 * q;
+      const float* M = a.pw + a.WhT[kk] + g * HP * HP;   // [32 j][32 i]
+      sWhcT[e] = make_float4(__ldg(M + n * HP + lane), __ldg(M + (n + 1) * HP + lane),
+                             __ldg(M + n * HP + (lane ^ 1)), __ldg(M + (n + 1) * HP + (lane ^ 1)));
+    }
+  } else if (CS_BWD) {
+    for (int e = tid; e < (L - 2) * 8 * HP; e += blockDim.x) {
+      const int kk = 2 + e / (8 * HP), q = (e / HP) % 8, lane = e % HP;
+      const int n = 16 * (lane & 1) + 2 * q;
+      const float* WcT = a.pw + a.WhT[kk] + 2 * HP * HP;   // [32 j][32 i]
+      sWhcT[e] = make_float4(__ldg(WcT + n * HP + lane), __ldg(WcT + (n + 1) * HP + lane),
+                             __ldg(WcT + n * HP + (lane ^ 1)), __ldg(WcT + (n + 1) * HP + (lane ^ 1)));
+    }
   }
   for (int e = tid; e < (L - 1) * nspc * HRS; e += blockDim.x) {
     mbar_init(&hand[e / HRS].full[e % HRS], 1);
@@ -1169,7 +1351,7 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     float* s_da0 = s_st0 + BNS0 * (BCH0 + 1) * ST;
     uint64_t* full0 = reinterpret_cast<uint64_t*>(s_da0 + 2 * BCH0 * G3 + 96);
     const L0BwdIo io{s_st0, s_da0, full0, a.st[0] + (int64_t)b * a.S[0] * ST, a.da[0] + (int64_t)b * a.S[0] * G3, a.S[0]};
-    wave_bwd_dx_helper(a, i, sWxT, &hand3[si], &hand[0 * nspc + si], io);
+    wave_bwd_dx_helper(a, i, UP ? nullptr : sWxT, &hand3[si], &hand[0 * nspc + si], io);
     return;
   }
   if (k == 0) {
@@ -1180,6 +1362,8 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
     unsigned char* reg1 = dsm + sm.l1 + si * bwd_region_bytes(BCH0, BNS0);
     if (hin == nullptr) wave_bwd_fast<false, true, false, DBG>(a, 1, b, i, reg1, nullptr, &hand3[si]);
     else wave_bwd_fast<true, true, false, DBG>(a, 1, b, i, reg1, hin, &hand3[si]);
+  } else if (UP) {                                       // k == 2: the upper warp walks layers 2 .. L-1
+    wave_bwd_upper<DBG>(a, b, i, dsm, sm, si, hout, sWxT, sWhcT);
   } else if (k == 2) {
     wave_bwd_layer<BCH2, BNSK, DBG>(a, k, b, i, dsm + sm.l2 + si * bwd_region_bytes(BCH2, BNSK), hin, hout,
                                     sWxT + (size_t)(k - 1) * 3 * 8 * HP, sWhcT + (size_t)(k - 2) * 8 * HP);
@@ -1189,28 +1373,32 @@ wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
   }
 }
 
+template <bool DBG, bool UP>
+static cudaError_t launch_wave_bwd_variant(const WaveBwdArgs& a, int grid, int threads, int smem, cudaStream_t st_) {
+  cudaFuncSetAttribute(wave_bwd_kernel<DBG, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return launch_pdl(wave_bwd_kernel<DBG, UP>, dim3(grid), dim3(threads), (size_t)smem, st_, a);   // prologue under the attention backward's tail
+}
+
 bool launch_wave_bwd(const Launch& L, const Dims& d, const PackLayout& pk, const float* pw, const float* const* st,
                      float* const* da, const float* dmemory, cudaStream_t st_) {
   if (d.L > WAVE_MAX_L || !wave_supported(d.L, d.P)) return false;
   const int nspc = d.L <= 5 ? 2 : 1;
-  const WaveBwdSmem sm(d.L, nspc);
+  static const bool up_env_off = [] { const char* e = getenv("HPMN_NO_BWD_UPPER"); return e && e[0] == '1'; }();
+  const bool up = BWD_UPPER && !up_env_off && d.L > 2;   // one warp for all layers >= 2 (8 warps per CTA, 255 registers)
+  const WaveBwdSmem sm(d.L, nspc, up);
   if (sm.total > 227 * 1024) return false;   // opt-in maximum of dynamic shared memory per CTA on sm_100
   WaveBwdArgs a; memset(&a, 0, sizeof(a));
   a.pw = pw; a.dmemory = dmemory;
   a.B = d.B; a.L = d.L; a.H = d.H; a.nspc = nspc;
   for (int k = 0; k < d.L; ++k) { a.st[k] = st[k]; a.da[k] = da[k]; a.WhT[k] = pk.WhT[k]; a.WxT[k] = pk.WxT[k]; a.S[k] = d.S[k]; a.P[k] = d.P[k]; }
   const int grid = (d.B + nspc - 1) / nspc;
-  const WarpPlan wp = plan_warps(d.L, nspc, d.L > 1, "HPMN_WAVE_WB");
+  // upper-warp mode plans three layer roles per sample (0, 1 and "2" = the upper warp) plus the helper
+  const WarpPlan wp = plan_warps(up ? 3 : d.L, nspc, d.L > 1, "HPMN_WAVE_WB");
   for (int i = 0; i < 16; ++i) { a.wlayer[i] = wp.layer[i]; a.wsample[i] = wp.sample[i]; a.whelper[i] = wp.helper[i]; }
   bool debug = false;
   { static int once = 0; const char* e = getenv("HPMN_WAVE_DEBUG"); debug = e && e[0] == '1' && once++ == 3; }   // 4th call only
-  if (debug) {
-    cudaFuncSetAttribute(wave_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    launch_pdl(wave_bwd_kernel<true>, dim3(grid), dim3(32 * wp.n), (size_t)sm.total, st_, a);
-  } else {
-    cudaFuncSetAttribute(wave_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    launch_pdl(wave_bwd_kernel<false>, dim3(grid), dim3(32 * wp.n), (size_t)sm.total, st_, a);   // ... the attention backward's tail
-  }
+  if (debug) { if (up) launch_wave_bwd_variant<true, true>(a, grid, 32 * wp.n, sm.total, st_); else launch_wave_bwd_variant<true, false>(a, grid, 32 * wp.n, sm.total, st_); }
+  else { if (up) launch_wave_bwd_variant<false, true>(a, grid, 32 * wp.n, sm.total, st_); else launch_wave_bwd_variant<false, false>(a, grid, 32 * wp.n, sm.total, st_); }
   { cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { if (getenv("HPMN_VERBOSE")) fprintf(stderr, "wave_bwd launch failed: %s (threads %d smem %d)\n", cudaGetErrorString(e), 32 * wp.n, sm.total); return false; } }
   ++*L.counter;
