@@ -42,6 +42,12 @@ def _worker(rank, world, port, B, q):
     g, dtb = O.backward(shl, f, ids[lo:hi], labels[lo:hi], memory_reg=1e-2, loss_scale_B=B)
     flat = torch.from_numpy(_flat(g, dtb))
     hd.allreduce_flat(flat)
+
+    class _Eng:                   # stand-in for HpmnEngine without a comm stream: allreduce_grads == the flat all-reduce
+        pass
+    eng = _Eng(); eng.flat_grad = torch.from_numpy(_flat(g, dtb)).clone(); eng.comm_stream = None
+    hd.allreduce_grads(eng)
+    assert torch.equal(eng.flat_grad, flat)
     scal = torch.tensor([f["logloss"] * (hi - lo) / B, f["covreg"]], dtype=torch.float64)
     hd.allreduce_scalars(scal)
     hd.barrier()
