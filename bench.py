@@ -46,7 +46,8 @@ def workload_name(cfg_name, cfg, B):
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions (and one untimed clock window of the
+    same step) run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -68,6 +69,9 @@ class ClockSampler:
     def stop(self, windows):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = time.time()
+        while len(self.rows) < 3 and time.time() - t0 < 3.0:      # a slow first nvidia-smi query must not leave the line without clocks
+            time.sleep(0.05)
         time.sleep(0.25)
         self.proc.terminate()
         inside = [r for (t, r) in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
@@ -198,12 +202,12 @@ def run_product(args, cfg_name, cfg):
         return float(ms.item()), (w0, w1)
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # before the warm-up: nvidia-smi needs ~0.5 s to deliver its first row, the timed regions are ~0.2 s each
     for i in range(args.warmup):
         step_dev(i)
     for i in range(min(args.warmup, 3)):
         step_host(i)
-    if rank == 0:
-        sampler.start()
     windows = []
     l0 = eng.launch_count()
     ms_dev, w = timed(step_dev, args.steps); windows.append(w)
@@ -214,6 +218,9 @@ def run_product(args, cfg_name, cfg):
     _, w = timed(step_dev, args.steps); windows.append(w)
     prof = eng.profile_read()
     eng.profile(False)
+    # clock window: the same step, untimed, for at least 0.6 s, so that the 100 ms sampler sees the load even when the timed
+    # regions above were shorter than its period (identical on every rank: the step contains the collective)
+    _, w = timed(step_dev, max(args.steps, int(0.6e3 / max(ms_dev / args.steps, 1e-3)))); windows.append(w)
     clocks = sampler.stop(windows) if rank == 0 else None
     scal = eng.scalars.cpu().numpy()
     if rank != 0:
