@@ -99,19 +99,34 @@ def oracle_inputs(cfg, B, seed_data=1234, seed_params=4321, V_cap=None):
     return sh, params, table, ids, labels
 
 
+NB = 8   # distinct id batches of the product arm (rotated so that no step re-reads its ids from L2)
+
+
+def make_config(cfg_name, cfg, B, world, keep_prob):
+    """`config` of the JSON line -- identical for the product and the reference arm (same workload, same step)."""
+    return {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world,
+            "parallelism": "dp%d batch-sharded, replicated table, one gradient exchange per step" % world,
+            "l2": "inputs larger than L2 (212 MB table + 0.56 GB streamed activations per step, %d rotating id batches)" % NB,
+            "keep_prob": keep_prob, "optimizer": "excluded (fwd+bwd metric)"}
+
+
 def run_reference(args, cfg_name, cfg):
-    """Reference arm: the reference's own CPU path.  TF1.4/py2 cannot be installed, so this is the
-    TF1-equivalent restatement (oracle/tf1_restatement.py, kind "port") on all host threads."""
+    """Reference arm: the reference's own CPU path on the SAME configuration as the product arm -- every row of the
+    B=256 batch, the full V x 16 table, T=1024 recurrence, dropout keep_prob of the train feed, fwd+bwd, optimizer
+    excluded.  TF1.4/py2 cannot be installed, so this is the TF1-equivalent restatement
+    (oracle/tf1_restatement.py, kind "port") on all host threads.  The table gradient is sparse (indices, rows), which
+    is what tf.gradients hands back for tf.nn.embedding_lookup (IndexedSlices) before the clip of code/hpmn.py:212."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import torch
     from oracle import tf1_restatement as R
-    rows = args.ref_rows
+    B = args.batch or cfg["batch"]
+    rows = args.ref_rows or B
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    # the table only matters through the rows touched; cap V so that the dense autograd table gradient stays cheap
-    sh, params, table, ids, labels = oracle_inputs(cfg, rows, V_cap=400000)
+    sh, params, table, ids, labels = oracle_inputs(cfg, rows)
     p = R._t(params, torch.float32)
     tb = torch.tensor(table, dtype=torch.float32, requires_grad=True)
     tid, tl = torch.tensor(ids, dtype=torch.int64), torch.tensor(labels, dtype=torch.float32)
@@ -121,19 +136,23 @@ def run_reference(args, cfg_name, cfg):
             v.grad = None
         tb.grad = None
         t0 = time.perf_counter()
-        out = R.forward_torch(sh, p, tb, tid, tl, memory_reg=cfg["memory_reg"])
+        masks = None
+        if args.keep_prob < 1.0:
+            masks = ((torch.rand(rows, 200) < args.keep_prob).float(), (torch.rand(rows, 80) < args.keep_prob).float())
+        out = R.forward_torch(sh, p, tb, tid, tl, cfg["memory_reg"], args.keep_prob, masks, sparse_grad=True)
         out["loss"].backward()
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     total = float(sum(times))
     value = rows * len(times) / total
-    B = args.batch or cfg["batch"]
-    sample = "%d of %d rows per step, full T=%d recurrence, fwd+bwd, fp32 torch-CPU op-per-timestep loop" % (rows, B, cfg["T"] + cfg["front_pad"])
+    sample = "%d of %d rows per step (%s), full V=%d table, full T=%d recurrence, fwd+bwd, fp32 torch-CPU op-per-timestep loop, sparse table gradient" % (
+        rows, B, "the whole batch" if rows == B else "a sample", sh.V, cfg["T"] + cfg["front_pad"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg_name, cfg, B), "sample_rows_per_step": rows,
-                       "note": "TF1-equivalent restatement, not TensorFlow (TF1.4/py2 not installable; DESIGN.md)"},
+            "config": make_config(cfg_name, cfg, B, max(world, args.gpus), args.keep_prob),
+            "note": "TF1-equivalent restatement, not TensorFlow (TF1.4/py2 not installable; DESIGN.md); one CPU process "
+                    "(rank 0) runs one rank's batch",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -157,8 +176,8 @@ def run_product(args, cfg_name, cfg):
                    last_offset=cfg["last_offset"])
     eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321)   # replicated parameters
     dev = eng.device
-    NB = 8   # distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
-    #          per-step working set is far larger than the 126 MB L2, so no explicit flush is needed
+    # NB distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
+    # per-step working set is far larger than the 126 MB L2, so no explicit flush is needed
     h_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + 97 * rank + i)).pin_memory() for i in range(NB)]
     h_lab = [torch.from_numpy(np.random.default_rng(99 + i + rank).integers(0, 2, size=B).astype(np.int32)).pin_memory()
              for i in range(NB)]
@@ -173,7 +192,7 @@ def run_product(args, cfg_name, cfg):
         eng.set_comm_stream(torch.cuda.Stream(device=dev))
 
     def step_dev(i):
-        eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=args.keep_prob, seed=i, loss_batch=loss_batch)
+        eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=args.keep_prob, seed=i * world + rank, loss_batch=loss_batch)
         if world > 1:
             hd.allreduce_grads(eng)                   # the step's single collective (flat [dense | table] buffer)
 
@@ -182,7 +201,7 @@ def run_product(args, cfg_name, cfg):
         # step still pays its own H2D + D2H inside the timed region
         if i == 0:
             eng.prefetch_host(h_ids[0], h_lab[0], B)
-        eng.step_host_pinned(True, args.keep_prob, i, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB], prefetch_next=(h_ids[(i + 1) % NB], h_lab[(i + 1) % NB]))
+        eng.step_host_pinned(True, args.keep_prob, i * world + rank, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB], prefetch_next=(h_ids[(i + 1) % NB], h_lab[(i + 1) % NB]))
         if world > 1:
             hd.allreduce_grads(eng)
 
@@ -278,12 +297,13 @@ def run_product(args, cfg_name, cfg):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import tf1_restatement as R
-        rows = args.cpu_rows
-        osh, params, table, ids, labels = oracle_inputs(cfg, rows, V_cap=400000)
-        r = R.time_cpu_baseline(osh, params, table, ids, labels, iters=3, warmup=1, budget_s=40)
+        rows = args.cpu_rows or B
+        osh, params, table, ids, labels = oracle_inputs(cfg, rows)
+        r = R.time_cpu_baseline(osh, params, table, ids, labels, iters=3, warmup=1, budget_s=40, memory_reg=cfg["memory_reg"],
+                                keep_prob=args.keep_prob, sparse_grad=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": "%d of %d rows, full T=%d recurrence, %d timed fwd+bwd passes, fp32 torch-CPU restatement of the TF1 "
-                         "graph (TensorFlow 1.4 itself is not installable here)" % (rows, B, sh.Tpad, r["iters"])}
+               "sample": "%d of %d rows, full V=%d table, full T=%d recurrence, %d timed fwd+bwd passes (median), fp32 torch-CPU "
+                         "restatement of the TF1 graph (TensorFlow 1.4 itself is not installable here)" % (rows, B, sh.V, sh.Tpad, r["iters"])}
     value = B * world * args.steps / (ms_dev * 1e-3)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = B * sh.T * sh.F * 4 + B * 4
@@ -291,10 +311,7 @@ def run_product(args, cfg_name, cfg):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world,
-                       "parallelism": "dp%d batch-sharded, replicated table, one flat all-reduce per step" % world,
-                       "l2": "inputs larger than L2 (212 MB table + 0.56 GB streamed activations per step, %d rotating id batches)" % NB,
-                       "keep_prob": args.keep_prob, "optimizer": "excluded (fwd+bwd metric)"},
+            "config": make_config(cfg_name, cfg, B, world, args.keep_prob),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "path": "hpmn_step_host (C ABI): pinned host ids/labels -> H2D (double-buffered via hpmn_prefetch_host) -> fwd+bwd -> D2H scalars,pred,logit,weights -> sync"},
@@ -313,8 +330,8 @@ def main():
     ap.add_argument("--config", default="xlong", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the config's)")
     ap.add_argument("--keep-prob", type=float, default=0.5, help="dropout keep prob of the train feed (code/hpmn.py:480)")
-    ap.add_argument("--cpu-rows", type=int, default=64)
-    ap.add_argument("--ref-rows", type=int, default=32)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the cpu_baseline sample (default: the whole batch)")
+    ap.add_argument("--ref-rows", type=int, default=0, help="rows per step of the reference arm (default: the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -3,7 +3,7 @@ B200-native engine.  DATASET is amazon | taobao | xlong with the reference's har
 
 Extra, optional flags (the reference has none): --data-root DIR (default ../data, the reference's relative
 layout), --synthetic N (train on N synthetic samples of the dataset's shape instead of reading files),
---epochs / --batchsize overrides, --out DIR for checkpoints and result.log."""
+--epochs / --batchsize / --eval-every overrides, --out DIR for checkpoints and result.log."""
 from __future__ import annotations
 
 import argparse
@@ -24,6 +24,9 @@ def main(argv=None):
     ap.add_argument("--synthetic", type=int, default=0)
     ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--batchsize", type=int, default=0)
+    ap.add_argument("--eval-every", type=int, default=0,
+                    help="evaluate / log every N steps (reference: 100 for amazon/taobao, 10 for xlong -- on the 2048-tuple "
+                         "sample file that is never reached, hpmn.py:483)")
     if argv is None and len(sys.argv) < 2:
         print("Useage: python hpmn.py [dataset]")   # sic, hpmn.py:565
         return 1
@@ -41,6 +44,8 @@ def main(argv=None):
             trainset, testset, feature_size = load_hpmn_pickle(os.path.join(a.data_root, "amazon/dataset_hpmn.pkl"))
         model = Hpmn(os.path.join(a.out, "amazon/hpmn/"), trainset, testset, feature_size, 3, 2, 100, 100, 0.003, 32, 16,
                      3, [2, 2, 5, 5, 1], [2, 2, 5, 5, 1], 3, 3, True, False, l2_reg=0., memory_reg=1e-5, max_batch=512)
+        if a.eval_every:
+            model.eval_every = a.eval_every
         best = model.train(a.epochs or 2, a.batchsize or 128)
         model.save_model()
     elif a.dataset == "taobao":                                 # hpmn.py:598-624
@@ -53,6 +58,8 @@ def main(argv=None):
             feature_size += 1   # the target btag id equals feature_size (preprocess_taobao.py:48,130,148)
         model = Hpmn(os.path.join(a.out, "taobao/hpmn/"), trainset, testset, feature_size, 4, 3, 300, 36, 0.001, 32, 16,
                      3, [2, 2, 3, 5, 5, 1], [2, 2, 3, 3, 1], 4, 5, True, False, l2_reg=0, memory_reg=1e-5, max_batch=512)
+        if a.eval_every:
+            model.eval_every = a.eval_every
         best = model.train(a.epochs or 2, a.batchsize or 128)
         model.save_model()
     elif a.dataset == "xlong":                                  # hpmn.py:627-664
@@ -75,6 +82,8 @@ def main(argv=None):
         model = Hpmn_Industry(os.path.join(a.out, "xlong/hpmn/"), train_set, test_set, feature_size, 2, 1, 1000 + 1, 184,
                               0.001, 32, 16, 3, [2] * 10 + [1], [3, 2, 2, 2, 2, 2, 2, 1], 5, 8, True, False,
                               emb_initializer, l2_reg=0, memory_reg=5e-5, max_batch=2048)
+        if a.eval_every:
+            model.eval_every = a.eval_every
         best = model.train(epochs=a.epochs or 3, batchsize=a.batchsize or 500)
         model.get_weights()
     else:

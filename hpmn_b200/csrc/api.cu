@@ -32,6 +32,7 @@ struct hpmn_ctx {
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
+  bool dtable_late;         // this step touches dtable after the scatter of the whole-batch chain (row groups, l2 term)
   // feed double buffering (hpmn_prefetch_host): copy stream, completion event, what is staged where
   cudaStream_t copy;
   cudaEvent_t ev_copy, ev_consumed[2];
@@ -567,7 +568,7 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
     { Bracket b(ctx, st, HPMN_K_SCATTER);
       launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids + (int64_t)r0 * d.T * d.F,
                         p.f(p.wl.dxk[0]), p.f(p.wl.dlast), dtable, st); }
-    if (side_ok && ctx->comm) {                          // whole-batch step: the table gradient is final from here on
+    if (side_ok && ctx->comm && !ctx->dtable_late) {     // whole-batch step: the table gradient is final from here on
       cudaEventRecord(ctx->ev_dtable, st);
       cudaStreamWaitEvent(ctx->comm, ctx->ev_dtable, 0);
     }
@@ -592,6 +593,9 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   int G = ctx->profile ? 1 : ctx->groups;
   while (G > 1 && d.B / G < ctx->group_min_rows) --G;
   ctx->zero_pending = false;
+  // the comm stream is told "dtable is final" right behind the scatter only when nothing else writes dtable afterwards:
+  // with row groups there are G scatters on G streams, and the l2 term adds l2_reg * table at the very end
+  ctx->dtable_late = G > 1 || hy.l2_reg != 0.f;
   // the weight repacking does not depend on the gather: it runs beside it on the side stream (ahead of the table-gradient
   // zeroing queued there below) and is joined in front of the projection GEMM
   const bool side_pack = G == 1 && ctx->overlap && !ctx->profile;
@@ -641,14 +645,21 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   { Bracket b(ctx, st, HPMN_K_MISC);
     launch_finish_scalars(L, scalars, hy.memory_reg, st);
     if (hy.l2_reg != 0.f) {   // l2_reg * tf.nn.l2_loss(v) over every trainable, code/hpmn.py:204-205
-      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(params, p.pl.total, 0.5f * hy.l2_reg, scalars + HPMN_S_LOSS);
-      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(table, s->V * (int64_t)d.E, 0.5f * hy.l2_reg, scalars + HPMN_S_LOSS);
+      // Under data parallelism every rank holds the same parameters and the gradients / scalars are SUMMED over ranks:
+      // each rank contributes its share B / loss_batch of the (batch-independent) l2 term, so the sum is exactly one l2 term.
+      const float l2 = hy.l2_reg * (float)d.B / (float)hy.loss_batch;
+      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(params, p.pl.total, 0.5f * l2, scalars + HPMN_S_LOSS);
+      sumsq_kernel<<<ctx->sms * 4, 256, 0, st>>>(table, s->V * (int64_t)d.E, 0.5f * l2, scalars + HPMN_S_LOSS);
       ctx->launches += 2;
       if (with_backward) {
-        launch_axpy(L, grads, params, hy.l2_reg, p.pl.total, st);
-        launch_axpy(L, dtable, table, hy.l2_reg, s->V * (int64_t)d.E, st);
+        launch_axpy(L, grads, params, l2, p.pl.total, st);
+        launch_axpy(L, dtable, table, l2, s->V * (int64_t)d.E, st);
       }
     } }
+  if (with_backward && ctx->comm && ctx->dtable_late) {   // every writer of dtable is joined into `st` by now
+    CK(cudaEventRecord(ctx->ev_dtable, st));
+    CK(cudaStreamWaitEvent(ctx->comm, ctx->ev_dtable, 0));
+  }
   return HPMN_OK;
 }
 

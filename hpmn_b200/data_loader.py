@@ -50,6 +50,9 @@ class DataLoader:
 
     next = __next__
 
+    def close(self):
+        pass
+
 
 XLONG_ITEM_CNT = 3269017   # data_loader.py:49
 XLONG_ITEM_LEN = 1000 + 1  # data_loader.py:56
@@ -82,23 +85,47 @@ class DataLoader_Mul:
         self.batch_size = batchsize // 2
         self.path = dataset
         self.q: "queue.Queue" = queue.Queue(maxsize=max_q_size)
+        self._stop = threading.Event()
         self.thread = threading.Thread(target=self._produce, daemon=True)
         self.thread.start()
 
+    def _put(self, item) -> bool:
+        while not self._stop.is_set():
+            try:
+                self.q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
     def _produce(self):
-        with open(self.path) as f:
-            while True:
-                lines = []
-                for _ in range(self.batch_size):
-                    line = f.readline()
-                    if not line:
+        """Always ends with a sentinel: None after the last batch, or the exception a malformed line raised (re-raised by
+        __next__, so a bad file fails the job instead of hanging it)."""
+        try:
+            with open(self.path) as f:
+                while not self._stop.is_set():
+                    lines = []
+                    for _ in range(self.batch_size):
+                        line = f.readline()
+                        if not line:
+                            break
+                        lines.append(line)
+                    if lines and not self._put((None, parse_xlong_lines(lines))):
+                        return
+                    if len(lines) < self.batch_size:
                         break
-                    lines.append(line)
-                if lines:
-                    self.q.put((None, parse_xlong_lines(lines)))
-                if len(lines) < self.batch_size:
-                    break
-        self.q.put(None)
+            self._put(None)
+        except BaseException as e:  # noqa: BLE001 -- forwarded to the consumer
+            self._put(e)
+
+    def close(self):
+        """Stop the producer and drop what it parsed ahead (train() leaving early on the early-stop rule, eval() done)."""
+        self._stop.set()
+        try:
+            while True:
+                self.q.get_nowait()
+        except queue.Empty:
+            pass
 
     def __iter__(self):
         return self
@@ -107,6 +134,8 @@ class DataLoader_Mul:
         item = self.q.get()
         if item is None:
             raise StopIteration
+        if isinstance(item, BaseException):
+            raise item
         return item
 
     next = __next__

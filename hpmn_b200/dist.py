@@ -33,6 +33,13 @@ def init_process_group(backend: str = "nccl") -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
+def rank_world() -> Tuple[int, int]:
+    """(rank, world) of the default process group; (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def shard_range(n_global: int, rank: int, world: int) -> Tuple[int, int]:
     """Rows [lo, hi) of the global batch owned by `rank` (contiguous, sizes differ by at most one)."""
     base, rem = divmod(n_global, world)
@@ -63,6 +70,12 @@ def allreduce_grads(eng) -> None:
         dist.all_reduce(eng.dtable, op=dist.ReduceOp.SUM)
     dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
     torch.cuda.current_stream(eng.device).wait_stream(comm)
+
+
+def exchange_grads(eng, ids=None) -> None:
+    """The step's gradient exchange for an HpmnEngine: after it every rank holds the sum over ranks of the dense gradients
+    and of the embedding-table gradient.  Default: the flat all-reduce (allreduce_grads)."""
+    allreduce_grads(eng)
 
 
 def allreduce_scalars(scalars: torch.Tensor) -> torch.Tensor:

@@ -200,6 +200,13 @@ class HpmnEngine:
         _lib.check(self.lib.hpmn_prefetch_host(self.ctx, C.byref(self._cshape(B)), _ptr(h_ids), _ptr(h_labels),
                                                _ptr(self.workspace)), self.ctx)
 
+    def check_ids(self):
+        """Device-path twin of the check hpmn_step_host_end does: forward / forward_backward embed an id outside
+        [0, feature_size) as zeros and drop its gradient (they cannot raise without a sync); this reads the flag the
+        gather left in scalars[3] (one 16-byte D2H, synchronises the stream) and raises like TF's GatherV2 does on CPU."""
+        if float(self.scalars[_lib.S_IDERR].item()) != 0.0:
+            raise _lib.HpmnError(_lib.HPMN_EINVAL, "an id is outside [0, feature_size=%d)" % self.shape.V)
+
     def apply_gradients(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, clip: float = 1.0):
         """clip_by_value(g,-1,1) + dense Adam over [dense params | table] (hpmn.py:209-214; the clip densifies the
         embedding gradient in TF1.4, so every table row is touched each step)."""

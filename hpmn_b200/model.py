@@ -80,15 +80,27 @@ class Hpmn_Basic(object):
 
     # ---- hpmn.py:91-111
     def save_model(self, global_step=None):
-        state = {"step": self.engine.adam_t, "table": self.engine.table.cpu(), "params": self.engine.named_parameters()}
+        """tf.train.Saver saves every variable INCLUDING the Adam slots and beta powers (hpmn.py:61-62,91-99), so a
+        resumed run continues the bias correction where it stopped.  Plain tensors only (loadable with weights_only=True)."""
+        eng = self.engine
+        state = {"step": torch.tensor(eng.adam_t), "table": eng.table.cpu()}
+        for name, arr in eng.named_parameters().items():
+            state["param:" + name] = torch.from_numpy(arr)
+        if eng.adam_m is not None:
+            state["adam_m"], state["adam_v"] = eng.adam_m.cpu(), eng.adam_v.cpu()
         path = self.save_path if global_step is None else "%s-%d" % (self.save_path, global_step)
         torch.save(state, path)
 
     def load_model(self):
         try:
-            state = torch.load(self.save_path, weights_only=False)
-            self.engine.load_named(state["params"])
-            self.engine.table.copy_(state["table"])
+            state = torch.load(self.save_path, weights_only=True)
+            eng = self.engine
+            eng.load_named({k[6:]: v.numpy() for k, v in state.items() if k.startswith("param:")})
+            eng.table.copy_(state["table"])
+            eng.adam_t = int(state["step"])
+            if "adam_m" in state:
+                eng.adam_m = state["adam_m"].to(eng.device)
+                eng.adam_v = state["adam_v"].to(eng.device)
         except Exception:
             raise IOError("Failed to load model from save path: %s" % self.save_path)
         print("Successfully load model from save path: %s" % self.save_path)
@@ -106,12 +118,23 @@ class Hpmn_Basic(object):
         return np.asarray(data[1], dtype=np.int32), np.asarray(data[0], dtype=np.int32)
 
     def train_on_batch(self, data):
+        """One `sess.run(train_step)` (hpmn.py:482).  Under torchrun (torch.distributed initialised, world > 1) the batch
+        rows are sharded across the ranks, every rank back-propagates its share of the GLOBAL-batch loss, the gradients
+        are exchanged once (hpmn_b200.dist.exchange_grads) and every rank applies the identical clip + Adam update."""
+        from . import dist as hd
         ids, labels = self._feed(data)
-        if len(labels) > self.max_batch:
-            raise ValueError("train batch %d exceeds max_batch=%d (pass a larger max_batch)" % (len(labels), self.max_batch))
+        n = len(labels)
+        rank, world = hd.rank_world()
+        lo, hi = hd.shard_range(n, rank, world)
+        if hi - lo > self.max_batch:
+            raise ValueError("train batch %d exceeds max_batch=%d (pass a larger max_batch)" % (hi - lo, self.max_batch))
         self._step_seed += 1
-        self.engine.step_host(ids, labels, with_backward=True, keep_prob=0.5, seed=self._step_seed)   # hpmn.py:480
-        self.engine.apply_gradients(self.learning_rate)                                                # hpmn.py:209-214
+        # dropout masks are keyed on (seed, local row): a distinct seed per rank keeps the shards' masks independent
+        self.engine.step_host(ids[lo:hi], labels[lo:hi], with_backward=True, keep_prob=0.5,                    # hpmn.py:480
+                              seed=self._step_seed * world + rank, loss_batch=n)
+        if world > 1:
+            hd.exchange_grads(self.engine)
+        self.engine.apply_gradients(self.learning_rate)                                                        # hpmn.py:209-214
 
     def predict_on_batch(self, data):
         """eval fetch; batches larger than the engine capacity are evaluated in chunks (rows are independent; the
@@ -128,32 +151,43 @@ class Hpmn_Basic(object):
 
     # ---- hpmn.py:467-495 / 322-349
     def train(self, epochs, batchsize):
+        from . import dist as hd
+        is_main = hd.rank_world()[0] == 0          # replicas are identical: every rank evaluates, rank 0 logs
         step, count, best = 0, 0, 0.0
         for _ in range(epochs):
-            for _, data in self.loader_cls(self.trainset, batchsize):
-                self.train_on_batch(data)
-                step += 1
-                if step % self.eval_every == 0:
-                    result = list(self.eval(self.trainset, 4 * batchsize))
-                    result += list(self.eval(self.testset, 4 * batchsize))
-                    self.log(step, result)
-                    if result[3] <= best:
-                        count += 1
-                        if count > 3:
-                            return best
-                    else:
-                        count = 0
-                        best = result[3]
+            loader = self.loader_cls(self.trainset, batchsize)
+            try:
+                for _, data in loader:
+                    self.train_on_batch(data)
+                    step += 1
+                    if step % self.eval_every == 0:
+                        result = list(self.eval(self.trainset, 4 * batchsize))
+                        result += list(self.eval(self.testset, 4 * batchsize))
+                        if is_main:
+                            self.log(step, result)
+                        if result[3] <= best:
+                            count += 1
+                            if count > 3:
+                                return best
+                        else:
+                            count = 0
+                            best = result[3]
+            finally:
+                loader.close()
         return best
 
     # ---- hpmn.py:497-519 / 351-373
     def eval(self, dataset, batchsize):
         labels, preds, mem_losses = [], [], []
-        for _, data in self.loader_cls(dataset, batchsize):
-            labels += list(data[0])
-            mem_loss, pred, _ = self.predict_on_batch(data)
-            mem_losses.append(mem_loss)
-            preds += pred.tolist()
+        loader = self.loader_cls(dataset, batchsize)
+        try:
+            for _, data in loader:
+                labels += list(data[0])
+                mem_loss, pred, _ = self.predict_on_batch(data)
+                mem_losses.append(mem_loss)
+                preds += pred.tolist()
+        finally:
+            loader.close()
         auc, loss = _metrics(labels, preds)
         return auc, loss, float(np.average(mem_losses))
 

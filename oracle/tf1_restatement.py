@@ -26,12 +26,14 @@ def _t(p: Dict[str, np.ndarray], dtype, requires_grad=True):
     return {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=requires_grad) for k, v in p.items()}
 
 
-def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_prob=1.0, masks=None):
-    """p: dict of torch tensors, table: torch [V,E]; ids: torch int64 [B,T,F]; labels: torch float [B]."""
+def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_prob=1.0, masks=None, sparse_grad=False):
+    """p: dict of torch tensors, table: torch [V,E]; ids: torch int64 [B,T,F]; labels: torch float [B].
+    sparse_grad: the table gradient is a sparse (indices, rows) tensor -- what tf.gradients returns for
+    tf.nn.embedding_lookup (IndexedSlices, before the clip of code/hpmn.py:212 densifies it)."""
     H, sc = sh.H, sh.scope
     B = ids.shape[0]
     # hpmn.py:414-430 / 266-282
-    x = torch.nn.functional.embedding(ids, table)
+    x = torch.nn.functional.embedding(ids, table, sparse=sparse_grad)
     if sh.mask_id0:
         x = x * (ids != 0).unsqueeze(-1).to(x.dtype)
     x = x.reshape(B, sh.T, sh.D)
@@ -47,8 +49,9 @@ def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_
         xt = inp.transpose(0, 1)                      # time-major like rnn.py:560-563
         h = torch.zeros(B, H, dtype=x.dtype)          # zero_state, rnn.py:588
         outs = []
-        for s in range(xt.shape[0]):                  # while_loop body, rnn.py:780-793
-            xs = xt[s]
+        # input_ta.unstack(input), rnn.py:722-725: one tensor per step (its gradient is a stack, O(T); indexing xt[s]
+        # would make autograd materialise a full-size zero tensor per step, O(T^2), which TF's TensorArray does not)
+        for xs in xt.unbind(0):                       # while_loop body, rnn.py:780-793
             g = torch.sigmoid(torch.matmul(torch.cat([xs, h], dim=1), Wg) + bg)
             r, u = torch.split(g, H, dim=1)
             c = torch.tanh(torch.matmul(torch.cat([xs, r * h], dim=1), Wc) + bc)
@@ -114,7 +117,7 @@ def forward_backward_numpy(sh: OracleShape, params, table, ids, labels, memory_r
 
 
 def time_cpu_baseline(sh: OracleShape, params, table, ids, labels, iters=3, warmup=1, threads=None,
-                      budget_s=None):
+                      budget_s=None, memory_reg=1e-5, keep_prob=1.0, sparse_grad=True):
     """fwd+bwd samples/sec of the restatement in fp32 on `threads` host threads (default: all).
     Returns dict(value, ms_per_step, cores, iters).  The optimizer is excluded, like the GPU arm."""
     import os
@@ -131,7 +134,10 @@ def time_cpu_baseline(sh: OracleShape, params, table, ids, labels, iters=3, warm
             v.grad = None
         tb.grad = None
         t0 = time.perf_counter()
-        out = forward_torch(sh, p, tb, tid, tl)
+        masks = None
+        if keep_prob < 1.0:      # tf.nn.dropout(keep_prob) of the train feed, code/hpmn.py:191-194,480
+            masks = ((torch.rand(ids.shape[0], 200) < keep_prob).float(), (torch.rand(ids.shape[0], 80) < keep_prob).float())
+        out = forward_torch(sh, p, tb, tid, tl, memory_reg, keep_prob, masks, sparse_grad=sparse_grad)
         out["loss"].backward()
         dt = time.perf_counter() - t0
         if i >= warmup:

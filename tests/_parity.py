@@ -1,6 +1,6 @@
 """Shared parity harness: run the CUDA path (through the C ABI) and the oracle on identical seeded
 inputs and report the error of every output and gradient.  Used by the -m gpu tests, by
-__graft_entry__.smoke() and by tests/gpu_report.py."""
+__graft_entry__.smoke()."""
 from __future__ import annotations
 
 import numpy as np
@@ -69,15 +69,19 @@ def run_case(sh, memory_reg=1e-3, mode="stress", ragged=True, seed_data=1234, se
     out["covreg"] = rel_max(scal[1], fwd["covreg"])
     out["loss"] = rel_max(scal[2], fwd["loss"])
     grads = eng.named_grads()
+    # per-tensor L2 error with the floor of tests/test_gpu_parity.py::_grad_close: a tensor whose true gradient is
+    # identically zero (the last attention-MLP bias: softmax is shift invariant) is measured against the scale of the
+    # largest gradient entry of the step instead of against its own ~1e-9 round-off
+    gmax = max(float(np.abs(v).max()) for v in g_ref.values())
     worst, worst_name = 0.0, ""
     for k, v in g_ref.items():
-        e = rel_l2(grads[k], v)
+        e = rel_l2(grads[k], v, floor=1e-4 * gmax)
         out["grad:" + k] = e
         if e > worst:
             worst, worst_name = e, k
     out["grad_worst"] = worst
     out["grad_worst_name"] = worst_name
-    out["dtable"] = rel_l2(eng.dtable.cpu().numpy(), dt_ref)
+    out["dtable"] = rel_l2(eng.dtable.cpu().numpy(), dt_ref, floor=1e-4 * gmax)
     out["launches"] = eng.launch_count()
     eng.close()
     return out

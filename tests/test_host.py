@@ -127,3 +127,33 @@ def test_model_signatures_match_reference():
         assert callable(getattr(model.Hpmn, m))
     assert (model.Hpmn.mask_id0, model.Hpmn.last_offset, model.Hpmn.eval_every) == (True, 1, 100)
     assert (model.Hpmn_Industry.mask_id0, model.Hpmn_Industry.last_offset, model.Hpmn_Industry.eval_every) == (False, 2, 10)
+
+
+def test_xlong_loader_forwards_a_parse_error_and_can_be_closed(tmp_path):
+    """A malformed line must fail the consumer (not hang it on an empty queue); close() releases a producer that is
+    blocked on a full queue (train() leaving early on the early-stop rule)."""
+    import time
+    from hpmn_b200.data_loader import DataLoader_Mul, write_synthetic_xlong
+    good = tmp_path / "good.txt"
+    write_synthetic_xlong(str(good), 6, hist=4, user_len=3)
+    bad = tmp_path / "bad.txt"
+    bad.write_text(good.read_text() + "7\tnot-a-uid\t1,2\t3\t4\t5\t6\n")
+    with pytest.raises(ValueError):
+        for _ in DataLoader_Mul(str(bad), 4):
+            pass
+    ld = DataLoader_Mul(str(good), 2, max_q_size=1)     # 6 batches of one line, queue of 1: the producer blocks
+    next(ld)
+    ld.close()
+    ld.thread.join(timeout=5)
+    assert not ld.thread.is_alive()
+
+
+def test_reference_arm_reports_the_product_arms_config():
+    """bench.py: both arms must describe the same workload (the driver compares `config`)."""
+    import bench
+    cfg = bench.CONFIGS["xlong"]
+    a = bench.make_config("xlong", cfg, 256, 1, 0.5)
+    assert a["global_batch"] == 256 and "V=3308019" in a["workload"] and "T=1001->1024" in a["workload"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("\"config\": make_config(cfg_name, cfg, B,") == 2          # one call per arm
+    assert "V_cap=" not in src.split("def run_reference")[1].split("def run_product")[0]

@@ -1,4 +1,4 @@
-"""python -m tests.probe_xlong [B] : time the XLong-shape step per kernel family (diagnostic)."""
+"""python -m tools.probe [B] [L] : time the XLong-shape step per kernel family (the command the ncu captures under profiles/ run; earlier rounds: tests.probe_xlong)."""
 import json
 import sys
 import time
