@@ -19,6 +19,8 @@ struct hpmn_ctx {
   bool wave_now;    // decided per step: the wavefront kernels are used only when the whole batch is one wave of CTAs
   bool use_wave;    // fused wavefront kernels for the recurrence (HPMN_NO_WAVE=1 selects the layer-by-layer kernels)
   bool use_tc;      // tcgen05 path for the dense (non-recurrent) GEMMs; HPMN_NO_TC=1 selects the FFMA kernels
+  int tcrec_mode;   // tensor-core recurrence (tcrec.cu): -1 auto (H > 32, or B >= tcrec_min_b), 0 never, 1 always (HPMN_TCREC)
+  int tcrec_min_b;  // HPMN_TCREC_MIN_B
   int device;
   int sms;
   int64_t launches;
@@ -152,7 +154,7 @@ static size_t group_stride(const hpmn_shape* s, int G) {
 static int make_plan(hpmn_ctx* ctx, const hpmn_shape* s, void* workspace, Plan& p) {
   if (!ctx) return HPMN_EINVAL;
   p.d = make_dims(s);
-  if (!p.d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape (need E%%4==0, H<=32, L<=16, hops<=8, steps divisible by periods)");
+  if (!p.d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape (need E%%4==0, H<=32 or H==64, L<=16, hops<=8, steps divisible by periods)");
   if (p.d.D > 64) return fail(ctx, HPMN_EINVAL, "F*E = %d > 64 is not supported by this build", p.d.D);
   for (int k = 0; k + 1 < p.d.L; ++k)
     if (p.d.P[k] > 16) return fail(ctx, HPMN_EINVAL, "period %d > 16 is not supported by this build", p.d.P[k]);
@@ -188,6 +190,97 @@ static void dense_gemm(hpmn_ctx* ctx, const Launch& L, const float* A, int64_t l
                        int64_t M, int N, int K, cudaStream_t st) {
   if (ctx->use_tc && launch_tc_gemm_nn(L, A, lda, W, bias, C, M, N, K, st)) return;
   launch_gemm_nn(L, A, lda, W, bias, C, M, N, K, st);
+}
+
+// tensor-core recurrence: chosen when the hidden size needs it or the batch fills M = 128 tiles on most SMs
+static bool want_tcrec(const hpmn_ctx* ctx, const Dims& d) {
+  if (!tcrec_supported(d)) return false;
+  if (d.H > HP) return true;
+  if (ctx->tcrec_mode >= 0) return ctx->tcrec_mode != 0;
+  return d.B >= ctx->tcrec_min_b;
+}
+
+// memory forward on tcgen05: pack, split x into the 3xTF32 halves, then one launch per layer
+static bool run_memory_fwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory, cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  const TcrLayout tl = make_tcr_layout(d);
+  if (!tl.ok) return false;
+  char* ws = p.ws + p.wl.tcr;
+  { Bracket b(ctx, st, HPMN_K_MISC); launch_tcr_pack(L, d, p.pl, tl, params, ws, st); }
+  { Bracket b(ctx, st, HPMN_K_INPROJ);
+    launch_tcr_split(L, x, reinterpret_cast<float*>(ws + tl.xh[0]), reinterpret_cast<float*>(ws + tl.xl[0]), (int64_t)d.B * d.S[0], d.D,
+                     tl.DP[0], st); }
+  Bracket b(ctx, st, HPMN_K_REC_FWD);
+  for (int k = 0; k < d.L; ++k)
+    if (!launch_tcrec_fwd(L, d, tl, k, ws, memory, st)) return false;
+  return true;
+}
+
+// memory backward on tcgen05: per layer (top first) the recurrent adjoint -> da_k, then dX_k = da_k Wx_k^T as a dense GEMM
+// (it is the dx_up of the layer below / the embedding gradient); the weight gradients of every layer in one launch at the end.
+// H = 32 reuses the dense kernels of the wavefront path (same h|r|u|c and r|u|c row layouts); H = 64 uses the FFMA GEMMs.
+static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, const float* dmemory, float* dx0,
+                              float* grads, cudaStream_t st) {
+  Launch L{&ctx->launches, ctx->sms};
+  const Dims& d = p.d;
+  const TcrLayout tl = make_tcr_layout(d);
+  if (!tl.ok) return false;
+  char* ws = p.ws + p.wl.tcr;
+  const int H = d.H;
+  const bool small = H <= HP;                       // the tcgen05 dX / weight-gradient kernels cover H <= 32
+  float* pw = p.f(p.wl.pw);
+  { Bracket b(ctx, st, HPMN_K_MISC);
+    launch_tcr_pack(L, d, p.pl, tl, params, ws, st);
+    if (small) launch_pack(L, d, p.pl, p.pk, params, pw, st); }
+  auto fp = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  for (int k = d.L - 1; k >= 0; --k) {
+    const float* dx_up = k < d.L - 1 ? fp(tl.dx[k + 1]) : nullptr;
+    { Bracket b(ctx, st, HPMN_K_REC_BWD);
+      if (!launch_tcrec_bwd(L, d, tl, k, ws, dmemory, dx_up, !small, st)) return false; }
+    { Bracket b(ctx, st, HPMN_K_DX);
+      float* dxk = k == 0 ? dx0 : fp(tl.dx[k]);
+      const int64_t rows = (int64_t)d.B * d.S[k];
+      if (small) {
+        dense_gemm(ctx, L, fp(tl.da[k]), G3, pw + p.pk.WxT[k], nullptr, dxk, rows, d.DinP[k], G3, st);
+      } else {
+        // dX[rows, Din] = da[rows, 3H] * [Wg_x | Wc_x]^T : two FFMA GEMMs against the TF-layout kernels (x rows), accumulated
+        launch_gemm_nt(L, fp(tl.da[k]), 3 * H, 0, params + p.pl.Wg[k], 2 * H, dxk, d.Din[k], rows, d.Din[k], 2 * H, false, st);
+        launch_gemm_nt(L, fp(tl.da[k]), 3 * H, 2 * H, params + p.pl.Wc[k], H, dxk, d.Din[k], rows, d.Din[k], H, true, st);
+      } }
+  }
+  Bracket b(ctx, st, HPMN_K_WGRAD);
+  if (small) {
+    const float* xa[HPMN_MAX_LAYERS]; int64_t lx[HPMN_MAX_LAYERS]; const float* stp[HPMN_MAX_LAYERS]; const float* dap[HPMN_MAX_LAYERS];
+    float *gWg[HPMN_MAX_LAYERS], *gbg[HPMN_MAX_LAYERS], *gWc[HPMN_MAX_LAYERS], *gbc[HPMN_MAX_LAYERS];
+    for (int k = 0; k < d.L; ++k) {
+      stp[k] = fp(tl.st[k]); dap[k] = fp(tl.da[k]);
+      xa[k] = k == 0 ? x : fp(tl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * ST;       // every p-th h row of the layer below
+      lx[k] = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
+      gWg[k] = grads + p.pl.Wg[k]; gbg[k] = grads + p.pl.bg[k]; gWc[k] = grads + p.pl.Wc[k]; gbc[k] = grads + p.pl.bc[k];
+    }
+    if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, st)))
+      for (int k = 0; k < d.L; ++k) launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], st);
+  } else {
+    // [x | h_prev]^T da_g, [x | r*h_prev]^T da_c, column sums: batched A^T B reductions (FFMA) over the rows of every layer
+    AtbBatch batch; batch.n = 0; batch.blocks = 0;
+    for (int k = 0; k < d.L; ++k) {
+      const int64_t rows = (int64_t)d.B * d.S[k];
+      const float* xin = k == 0 ? x : fp(tl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * 4 * H;
+      const int64_t ldx = k == 0 ? d.D : (int64_t)d.P[k - 1] * 4 * H;
+      const float* da = fp(tl.da[k]); const float* hr = fp(tl.hr[k]);
+      float* gWg = grads + p.pl.Wg[k]; float* gWc = grads + p.pl.Wc[k];
+      atb_add(batch, ctx->sms, xin, ldx, da, 3 * H, gWg, 2 * H, rows, d.Din[k], 2 * H);
+      atb_add(batch, ctx->sms, hr, 2 * H, da, 3 * H, gWg + (int64_t)d.Din[k] * 2 * H, 2 * H, rows, H, 2 * H);
+      atb_add(batch, ctx->sms, xin, ldx, da + 2 * H, 3 * H, gWc, H, rows, d.Din[k], H);
+      atb_add(batch, ctx->sms, hr + H, 2 * H, da + 2 * H, 3 * H, gWc + (int64_t)d.Din[k] * H, H, rows, H, H);
+      atb_add(batch, ctx->sms, nullptr, 0, da, 3 * H, grads + p.pl.bg[k], 2 * H, rows, 1, 2 * H);
+      atb_add(batch, ctx->sms, nullptr, 0, da + 2 * H, 3 * H, grads + p.pl.bc[k], H, rows, 1, H);
+      if (batch.n + 6 > ATB_MAX) { launch_atb_batch(L, batch, st); batch.n = 0; batch.blocks = 0; }
+    }
+    launch_atb_batch(L, batch, st);
+  }
+  return true;
 }
 
 // memory forward: pack + per layer (projection GEMM, recurrence)
@@ -312,6 +405,8 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx->profile = false; ctx->pool_used = 0; ctx->wave_now = true;
   { const char* e_tc = getenv("HPMN_NO_TC"); ctx->use_tc = !(e_tc && e_tc[0] == '1'); }
   { const char* e_w = getenv("HPMN_NO_WAVE"); ctx->use_wave = !(e_w && e_w[0] == '1'); }
+  { const char* e_t = getenv("HPMN_TCREC"); ctx->tcrec_mode = e_t ? atoi(e_t) : -1;
+    const char* e_b = getenv("HPMN_TCREC_MIN_B"); ctx->tcrec_min_b = e_b ? atoi(e_b) : 2048; }
   memset(ctx->ms, 0, sizeof(ctx->ms)); memset(ctx->calls, 0, sizeof(ctx->calls));
   cudaSetDevice(device);
   e = cudaMalloc(&ctx->scratch, 256);
@@ -445,7 +540,12 @@ int hpmn_memory_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const fl
   if (rc) return rc;
   if (!x || !params || !memory) return fail(ctx, HPMN_EINVAL, "NULL buffer");
   { const int nspc = p.d.L <= 5 ? 2 : 1; ctx->wave_now = (p.d.B + nspc - 1) / nspc <= ctx->sms; }
-  run_memory_fwd(ctx, p, x, params, memory, (cudaStream_t)stream);
+  if (want_tcrec(ctx, p.d)) {
+    if (!run_memory_fwd_tc(ctx, p, x, params, memory, (cudaStream_t)stream))
+      return fail(ctx, HPMN_ECUDA, "tensor-core recurrence could not be launched (tensor map / shared memory)");
+  } else {
+    run_memory_fwd(ctx, p, x, params, memory, (cudaStream_t)stream);
+  }
   return check_launch(ctx, "hpmn_memory_fwd");
 }
 
@@ -456,8 +556,13 @@ int hpmn_memory_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const fl
   if (!x || !params || !dmemory || !dx || !grads) return fail(ctx, HPMN_EINVAL, "NULL buffer");
   cudaStream_t st = (cudaStream_t)stream;
   Launch L{&ctx->launches, ctx->sms};
-  launch_pack(L, p.d, p.pl, p.pk, params, p.f(p.wl.pw), st);
+  if (p.d.H <= HP) launch_pack(L, p.d, p.pl, p.pk, params, p.f(p.wl.pw), st);
   { const int nspc = p.d.L <= 5 ? 2 : 1; ctx->wave_now = (p.d.B + nspc - 1) / nspc <= ctx->sms; }
+  if (want_tcrec(ctx, p.d)) {
+    if (!run_memory_bwd_tc(ctx, p, x, params, dmemory, dx, grads, st))
+      return fail(ctx, HPMN_ECUDA, "tensor-core recurrence could not be launched (tensor map / shared memory)");
+    return check_launch(ctx, "hpmn_memory_bwd");
+  }
   run_memory_bwd(ctx, p, x, dmemory, dx, grads, ctx->overlap && !ctx->profile, st);
   return check_launch(ctx, "hpmn_memory_bwd");
 }
@@ -791,6 +896,13 @@ int hpmn_debug_wgrad(hpmn_ctx* ctx, const hpmn_shape* s, int k, const float* xin
     launch_gru_wgrad(L, d, k, xin, ldx, st, da, dWg, dbg, dWc, dbc, (cudaStream_t)stream);
   }
   return check_launch(ctx, "hpmn_debug_wgrad");
+}
+
+int hpmn_debug_tcr_stamps(long long* out_host, int n) {
+  long long* buf = tcr_debug_buffer();
+  if (!buf || !out_host || n <= 0) return HPMN_EINVAL;
+  if (n > 2048 * 16) n = 2048 * 16;
+  return cudaMemcpy(out_host, buf, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? HPMN_OK : HPMN_ECUDA;
 }
 
 int hpmn_clip_adam(hpmn_ctx* ctx, float* var, const float* grad, float* m, float* v, int64_t n, int64_t t, float lr,

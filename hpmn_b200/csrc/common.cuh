@@ -10,7 +10,7 @@
 
 namespace hpmn {
 
-constexpr int HP = 32;        // hidden width padded to one warp (this build: H <= 32)
+constexpr int HP = 32;        // hidden width padded to one warp (warp-per-sample kernels: H <= 32; H = 64: tcrec.cu only)
 constexpr int G3 = 3 * HP;    // r | u | c columns of a packed gate row
 constexpr int ST = 4 * HP;    // h | r | u | c columns of a saved state row
 constexpr int ATT1 = 80;      // code/hpmn.py:137
@@ -39,7 +39,7 @@ inline Dims make_dims(const hpmn_shape* s) {
   Dims d; memset(&d, 0, sizeof(d));
   d.ok = false;
   if (!s) return d;
-  if (s->B <= 0 || s->T <= 0 || s->F <= 0 || s->E <= 0 || (s->E & 3) || s->H <= 0 || s->H > HP) return d;
+  if (s->B <= 0 || s->T <= 0 || s->F <= 0 || s->E <= 0 || (s->E & 3) || s->H <= 0 || (s->H > HP && s->H != 64)) return d;
   if (s->L <= 0 || s->L > HPMN_MAX_LAYERS || s->hops <= 0 || s->hops > HPMN_MAX_HOPS) return d;
   if (s->front_pad < 0 || s->last_offset < 1 || s->V <= 0) return d;
   d.B = s->B; d.T = s->T; d.Tpad = s->T + s->front_pad; d.F = s->F; d.E = s->E; d.D = s->F * s->E;
@@ -128,8 +128,26 @@ struct WsLayout {
   size_t head_a2, head_act2, head_dl2;// [B,80]
   size_t head_dlogit;                 // [B]
   size_t pred, logit, w_hop0, scalars;// outputs staging
+  size_t tcr;                         // base of the tensor-core recurrence region (aliases proj/st/dxk: one path runs per call)
   size_t total;
 };
+
+// workspace of the tensor-core recurrence (tcrec.cu); byte offsets relative to WsLayout::tcr
+struct TcrLayout {
+  bool ok;
+  int DP[HPMN_MAX_LAYERS];                              // padded input width of layer k (multiple of 32)
+  size_t wf[HPMN_MAX_LAYERS], bf[HPMN_MAX_LAYERS];      // forward weights [6H][DP+H] (hi rows, lo rows), scaled bias [3H]
+  size_t wb[HPMN_MAX_LAYERS];                           // backward weights [6H][H]: Wc_h^T | Wu_h^T | Wr_h^T, hi rows then lo rows
+  size_t xh[HPMN_MAX_LAYERS], xl[HPMN_MAX_LAYERS];      // [B,S_k,DP] hi / lo halves of the layer input
+  size_t st[HPMN_MAX_LAYERS];                           // [B,S_k,4H] h | r | u | c
+  size_t da[HPMN_MAX_LAYERS];                           // [B,S_k,3H]
+  size_t dx[HPMN_MAX_LAYERS];                           // [B,S_k,DP]
+  size_t hr[HPMN_MAX_LAYERS];                           // [B,S_k,2H] h_prev | r*h_prev (weight-gradient operands)
+  size_t total;
+};
+struct Dims;
+bool tcrec_supported(const Dims&);
+TcrLayout make_tcr_layout(const Dims&);
 
 struct PackLayout {                    // float offsets inside the packed-weights block
   int64_t Wx[HPMN_MAX_LAYERS];        // [DinP, 96]  input weights, cols g*32+j
@@ -163,11 +181,19 @@ inline WsLayout make_ws_layout(const Dims& d) {
   w.labels = take((size_t)d.B * sizeof(int32_t));
   w.x = take((size_t)d.B * d.Tpad * d.D * f);
   w.pw = take((size_t)make_pack_layout(d).total * f);
-  for (int k = 0; k < d.L; ++k) {
-    size_t rows = (size_t)d.B * d.S[k];
-    w.proj[k] = take(rows * G3 * f);
-    w.st[k] = take(rows * ST * f);
-    w.dxk[k] = take(rows * (k == 0 ? d.D : HP) * f);
+  off = (off + 1023) & ~(size_t)1023;
+  w.tcr = off;
+  if (d.H <= HP) {
+    for (int k = 0; k < d.L; ++k) {
+      size_t rows = (size_t)d.B * d.S[k];
+      w.proj[k] = take(rows * G3 * f);
+      w.st[k] = take(rows * ST * f);
+      w.dxk[k] = take(rows * (k == 0 ? d.D : HP) * f);
+    }
+  }
+  {
+    const TcrLayout t = make_tcr_layout(d);
+    if (t.ok && w.tcr + t.total > off) off = w.tcr + t.total;
   }
   w.memory = take((size_t)d.B * d.L * d.H * f);
   w.dmemory = take((size_t)d.B * d.L * d.H * f);
@@ -323,6 +349,9 @@ void launch_pack(const Launch&, const Dims&, const ParamLayout&, const PackLayou
 // C[M,N] = A[M,K](row stride lda) * W[K,N] (+ bias[N]); N, K multiples of 4
 void launch_gemm_nn(const Launch&, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
                     int N, int K, cudaStream_t st);
+// C[M,N](ldc) (+)= A[M, a0:a0+K](lda) * W[N,K](ldw)^T, fp32 FFMA (fallback where no tcgen05 instantiation exists)
+void launch_gemm_nt(const Launch&, const float* A, int64_t lda, int a0, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                    int N, int K, bool accumulate, cudaStream_t st);
 // same contract on tcgen05 tensor cores (3xTF32); returns false when (K,N) has no instantiation
 bool launch_tc_gemm_nn(const Launch&, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t M,
                        int N, int K, cudaStream_t st);
@@ -344,6 +373,14 @@ struct AtbBatch { int n; int blocks; AtbProb p[ATB_MAX]; };
 void atb_add(AtbBatch& batch, int sms, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
              int64_t M, int I, int N);
 void launch_atb_batch(const Launch&, const AtbBatch& batch, cudaStream_t st);
+
+// tensor-core recurrence (tcrec.cu).  ws = base of the TcrLayout region.
+void launch_tcr_pack(const Launch&, const Dims&, const ParamLayout&, const TcrLayout&, const float* params, char* ws, cudaStream_t st);
+void launch_tcr_split(const Launch&, const float* x, float* xh, float* xl, int64_t rows, int D, int DP, cudaStream_t st);
+long long* tcr_debug_buffer();
+bool launch_tcrec_bwd(const Launch&, const Dims&, const TcrLayout&, int k, char* ws, const float* dmemory, const float* dx_up,
+                      bool write_hr, cudaStream_t st);
+bool launch_tcrec_fwd(const Launch&, const Dims&, const TcrLayout&, int k, char* ws, float* memory, cudaStream_t st);
 
 void launch_rec_fwd(const Launch&, const Dims&, int k, const float* proj, const float* Wh, float* st, float* memory,
                     cudaStream_t st_);

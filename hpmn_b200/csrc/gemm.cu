@@ -172,6 +172,40 @@ void launch_gemm_nn(const Launch& L, const float* A, int64_t lda, const float* W
 }
 
 // ---------------------------------------------------------------------------------------------
+// C[M,N] (+)= A[M, a0 : a0+K] * W[N,K]^T   (W row-major [N rows, ldw], i.e. the x rows of a TF kernel used transposed).
+// Plain FFMA, one thread per output element group; only used where no tcgen05 instantiation exists (H = 64 dX).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const float* __restrict__ A, int64_t lda, int a0, const float* __restrict__ W, int64_t ldw, float* __restrict__ C,
+               int64_t ldc, int64_t M, int N, int K, int accumulate) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                                  // [N][K+1]
+  for (int e = threadIdx.x; e < N * K; e += 256) Ws[(e / K) * (K + 1) + e % K] = W[(int64_t)(e / K) * ldw + e % K];
+  __syncthreads();
+  const int64_t total = M * N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t m = e / N; const int n = (int)(e % N);
+    const float* a = A + m * lda + a0;
+    const float* w = Ws + n * (K + 1);
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(a[k], w[k], acc);
+    if (accumulate) C[m * ldc + n] += acc; else C[m * ldc + n] = acc;
+  }
+}
+
+void launch_gemm_nt(const Launch& L, const float* A, int64_t lda, int a0, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                    int N, int K, bool accumulate, cudaStream_t st) {
+  const size_t smem = (size_t)N * (K + 1) * sizeof(float);
+  cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int64_t blocks = (M * N + 255) / 256;
+  if (blocks > (int64_t)L.sms * 8) blocks = (int64_t)L.sms * 8;
+  if (blocks < 1) blocks = 1;
+  gemm_nt_kernel<<<(unsigned)blocks, 256, smem, st>>>(A, lda, a0, W, ldw, C, ldc, M, N, K, accumulate ? 1 : 0);
+  ++*L.counter;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched  C[I,N] += sum_m A[m,I] * Bm[m,N]  (weight gradients of the dense layers: reductions over
 // the batch rows).  One launch serves a list of problems; each CTA owns one 64x64 output tile of one
 // problem over one slice of the rows and finishes with atomics.  A == nullptr means a column of ones

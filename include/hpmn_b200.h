@@ -194,6 +194,11 @@ const char* hpmn_kernel_family_name(int family);
 int hpmn_debug_wgrad(hpmn_ctx*, const hpmn_shape*, int k, const float* xin, int64_t ldx, const float* st, const float* da,
                      float* grads, int use_tc, void* stream);
 
+/* HPMN_TCR_DEBUG=1 in the environment: the tensor-core recurrence (layer 0, CTA 0) stamps clock64 at the hand-offs of
+ * every step -- [t][0..7] epilogue warp 0, [t][8..15] MMA-issuing thread; copies n of the 2048 x 16 stamps to the host
+ * (synchronises the device).  HPMN_EINVAL when the hook is off.  Profiling aid (profiles/r2_tcrec_*.md). */
+int hpmn_debug_tcr_stamps(long long* out_host, int n);
+
 #ifdef __cplusplus
 }
 #endif
