@@ -201,13 +201,16 @@ static bool want_tcrec(const hpmn_ctx* ctx, const Dims& d) {
 }
 
 // memory forward on tcgen05: pack, split x into the 3xTF32 halves, then one launch per layer
-static bool run_memory_fwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory, cudaStream_t st) {
+static bool run_memory_fwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory, cudaStream_t st,
+                              bool packed_old = false) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   const TcrLayout tl = make_tcr_layout(d);
   if (!tl.ok) return false;
   char* ws = p.ws + p.wl.tcr;
-  { Bracket b(ctx, st, HPMN_K_MISC); launch_tcr_pack(L, d, p.pl, tl, params, ws, st); }
+  { Bracket b(ctx, st, HPMN_K_MISC);
+    launch_tcr_pack(L, d, p.pl, tl, params, ws, st);
+    if (!packed_old && d.H <= HP) launch_pack(L, d, p.pl, p.pk, params, p.f(p.wl.pw), st); }   // dense kernels of the backward pass
   { Bracket b(ctx, st, HPMN_K_INPROJ);
     launch_tcr_split(L, x, reinterpret_cast<float*>(ws + tl.xh[0]), reinterpret_cast<float*>(ws + tl.xl[0]), (int64_t)d.B * d.S[0], d.D,
                      tl.DP[0], st); }
@@ -221,7 +224,7 @@ static bool run_memory_fwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, cons
 // (it is the dx_up of the layer below / the embedding gradient); the weight gradients of every layer in one launch at the end.
 // H = 32 reuses the dense kernels of the wavefront path (same h|r|u|c and r|u|c row layouts); H = 64 uses the FFMA GEMMs.
 static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, const float* dmemory, float* dx0,
-                              float* grads, cudaStream_t st) {
+                              float* grads, cudaStream_t st, bool packed = false) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   const TcrLayout tl = make_tcr_layout(d);
@@ -230,9 +233,11 @@ static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, cons
   const int H = d.H;
   const bool small = H <= HP;                       // the tcgen05 dX / weight-gradient kernels cover H <= 32
   float* pw = p.f(p.wl.pw);
-  { Bracket b(ctx, st, HPMN_K_MISC);
+  if (!packed) {
+    Bracket b(ctx, st, HPMN_K_MISC);
     launch_tcr_pack(L, d, p.pl, tl, params, ws, st);
-    if (small) launch_pack(L, d, p.pl, p.pk, params, pw, st); }
+    if (small) launch_pack(L, d, p.pl, p.pk, params, pw, st);
+  }
   auto fp = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   for (int k = d.L - 1; k >= 0; --k) {
     const float* dx_up = k < d.L - 1 ? fp(tl.dx[k + 1]) : nullptr;
@@ -634,7 +639,8 @@ static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
     launch_gather_fwd(L, d, s->mask_id0 != 0, s->front_pad, s->V, ids + (int64_t)r0 * d.T * d.F, table, x,
                       scalars + HPMN_S_IDERR, st); }
   if (ov) cudaStreamWaitEvent(st, ctx->ev_join, 0);
-  run_memory_fwd(ctx, p, x, params, memory, st, ov);
+  if (!(want_tcrec(ctx, d) && run_memory_fwd_tc(ctx, p, x, params, memory, st, ov)))
+    run_memory_fwd(ctx, p, x, params, memory, st, ov);
   { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
     launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L,
                     scalars, p.att(), st); }
@@ -652,6 +658,9 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   float* x = p.f(p.wl.x);
   const float* memory = p.hf(p.hdr.memory) + (int64_t)r0 * d.L * d.H;
   const bool ov = side_ok && ctx->overlap && !ctx->profile;
+  // the tensor-core recurrence keeps its own activations (they alias the wavefront path's: one of the two runs per call)
+  const bool tc = want_tcrec(ctx, d);
+  float* dx0 = tc ? reinterpret_cast<float*>(p.ws + p.wl.tcr + make_tcr_layout(d).dx[0]) : p.f(p.wl.dxk[0]);
   AtbBatch batch; batch.n = 0; batch.blocks = 0;
   { Bracket b(ctx, st, HPMN_K_HEAD_BWD);
     launch_head_bwd(L, d, p.pl, hy, r0, p.f(p.wl.repre), labels + r0, params, p.hf(p.hdr.pred) + r0, p.f(p.wl.drepre), grads,
@@ -672,13 +681,19 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
     if (ctx->zero_pending) { cudaStreamWaitEvent(st, ctx->ev_zero, 0); ctx->zero_pending = false; }
     { Bracket b(ctx, st, HPMN_K_SCATTER);
       launch_gather_bwd(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, ids + (int64_t)r0 * d.T * d.F,
-                        p.f(p.wl.dxk[0]), p.f(p.wl.dlast), dtable, st); }
+                        dx0, p.f(p.wl.dlast), dtable, st); }
     if (side_ok && ctx->comm && !ctx->dtable_late) {     // whole-batch step: the table gradient is final from here on
       cudaEventRecord(ctx->ev_dtable, st);
       cudaStreamWaitEvent(ctx->comm, ctx->ev_dtable, 0);
     }
   };
-  run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), p.f(p.wl.dxk[0]), grads, ov, st, false, scatter);
+  if (tc) {
+    // tensor-core recurrence: everything on `st` (its dense kernels fill the machine at the batch sizes that select it)
+    run_memory_bwd_tc(ctx, p, x, params, p.f(p.wl.dmemory), dx0, grads, st, true);
+    scatter();
+  } else {
+    run_memory_bwd(ctx, p, x, p.f(p.wl.dmemory), dx0, grads, ov, st, false, scatter);
+  }
   if (ov) { cudaEventRecord(ctx->ev_join, ctx->side); cudaStreamWaitEvent(st, ctx->ev_join, 0); }
 }
 
@@ -688,6 +703,9 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
                     float* scalars, cudaStream_t st) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
+  if (d.H > HP)
+    return fail(ctx, HPMN_EINVAL, "hidden_size %d > 32: this build covers it in hpmn_memory_fwd / hpmn_memory_bwd (tensor-core recurrence) "
+                                  "only; the attention / head kernels are written for H <= 32", d.H);
   if (hy.loss_batch <= 0) hy.loss_batch = d.B;          // the groups must divide the log-loss by the whole batch
   // Wavefront kernels: 2 samples per CTA (1 for L > 5), one CTA per SM (shared memory).  They minimise the latency of
   // one wave; with more samples than one wave holds, the per-layer kernels (one warp per sample, ~12 resident per SM)
