@@ -174,7 +174,9 @@ def run_product(args, cfg_name, cfg):
     sh = HpmnShape(B=B, T=cfg["T"], F=cfg["F"], E=cfg["E"], H=cfg["H"], periods=cfg["periods"], L=cfg["L"],
                    hops=cfg["hops"], V=cfg["V"], front_pad=cfg["front_pad"], mask_id0=cfg["mask_id0"],
                    last_offset=cfg["last_offset"])
-    eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321)   # replicated parameters
+    eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321, symmetric=world > 1)   # replicated parameters
+    exch = hd.GradExchange(eng, mode=os.environ.get("HPMN_EXCHANGE", "auto"))
+    eng.exchange = exch
     dev = eng.device
     # NB distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
     # per-step working set is far larger than the 126 MB L2, so no explicit flush is needed
@@ -185,16 +187,10 @@ def run_product(args, cfg_name, cfg):
     d_lab = [t.to(dev) for t in h_lab]
     loss_batch = B * world
 
-    if world > 1 and os.environ.get("HPMN_COMM_OVERLAP") == "1":
-        # experiment (off by default): start the table-gradient all-reduce as soon as the scatter is done, beside the GRU
-        # weight-gradient reduction.  Measured at N=2: 1.3227 vs 1.3253 ms -- the second collective and the contention with the
-        # weight-gradient kernel eat the ~110 us head start (profiles/r1_v8_wave_step_timeline.md, section 5)
-        eng.set_comm_stream(torch.cuda.Stream(device=dev))
-
     def step_dev(i):
         eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=args.keep_prob, seed=i * world + rank, loss_batch=loss_batch)
         if world > 1:
-            hd.allreduce_grads(eng)                   # the step's single collective (flat [dense | table] buffer)
+            hd.exchange_grads(eng)                    # the step's gradient exchange (GradExchange: peer rows / in-switch all-reduce)
 
     def step_host(i):
         # the feed of step i+1 is staged on the library's copy stream while step i computes (double-buffered H2D); every
@@ -203,7 +199,7 @@ def run_product(args, cfg_name, cfg):
             eng.prefetch_host(h_ids[0], h_lab[0], B)
         eng.step_host_pinned(True, args.keep_prob, i * world + rank, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB], prefetch_next=(h_ids[(i + 1) % NB], h_lab[(i + 1) % NB]))
         if world > 1:
-            hd.allreduce_grads(eng)
+            hd.exchange_grads(eng)
 
     def timed(fn, steps):
         hd.barrier(); torch.cuda.synchronize(dev)
@@ -312,6 +308,7 @@ def run_product(args, cfg_name, cfg):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": make_config(cfg_name, cfg, B, world, args.keep_prob),
+            "exchange": {"mode": exch.mode, "why": exch.why},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "path": "hpmn_step_host (C ABI): pinned host ids/labels -> H2D (double-buffered via hpmn_prefetch_host) -> fwd+bwd -> D2H scalars,pred,logit,weights -> sync"},

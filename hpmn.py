@@ -32,8 +32,16 @@ def main(argv=None):
         return 1
     a = ap.parse_args(argv)
 
+    from hpmn_b200 import dist as hd
     from hpmn_b200.data_loader import load_hpmn_pickle, synthetic_dataset
     from hpmn_b200.model import Hpmn, Hpmn_Industry
+
+    # `torchrun --nproc-per-node N hpmn.py DATASET`: one process per GPU, every batch sharded by rows, gradients exchanged once
+    # per step (the reference is single-process; without torchrun this is rank 0 of 1)
+    rank, local_rank, world = hd.env_world()
+    if world > 1:
+        hd.init_process_group("nccl")
+    dev = dict(device=local_rank)
 
     if a.dataset == "amazon":                                   # hpmn.py:570-596
         if a.synthetic:
@@ -43,11 +51,12 @@ def main(argv=None):
         else:
             trainset, testset, feature_size = load_hpmn_pickle(os.path.join(a.data_root, "amazon/dataset_hpmn.pkl"))
         model = Hpmn(os.path.join(a.out, "amazon/hpmn/"), trainset, testset, feature_size, 3, 2, 100, 100, 0.003, 32, 16,
-                     3, [2, 2, 5, 5, 1], [2, 2, 5, 5, 1], 3, 3, True, False, l2_reg=0., memory_reg=1e-5, max_batch=512)
+                     3, [2, 2, 5, 5, 1], [2, 2, 5, 5, 1], 3, 3, True, False, l2_reg=0., memory_reg=1e-5, max_batch=512, **dev)
         if a.eval_every:
             model.eval_every = a.eval_every
         best = model.train(a.epochs or 2, a.batchsize or 128)
-        model.save_model()
+        if rank == 0:
+            model.save_model()
     elif a.dataset == "taobao":                                 # hpmn.py:598-624
         if a.synthetic:
             feature_size = 4000000
@@ -57,11 +66,12 @@ def main(argv=None):
             trainset, testset, feature_size = load_hpmn_pickle(os.path.join(a.data_root, "taobao/dataset_hpmn.pkl"))
             feature_size += 1   # the target btag id equals feature_size (preprocess_taobao.py:48,130,148)
         model = Hpmn(os.path.join(a.out, "taobao/hpmn/"), trainset, testset, feature_size, 4, 3, 300, 36, 0.001, 32, 16,
-                     3, [2, 2, 3, 5, 5, 1], [2, 2, 3, 3, 1], 4, 5, True, False, l2_reg=0, memory_reg=1e-5, max_batch=512)
+                     3, [2, 2, 3, 5, 5, 1], [2, 2, 3, 3, 1], 4, 5, True, False, l2_reg=0, memory_reg=1e-5, max_batch=512, **dev)
         if a.eval_every:
             model.eval_every = a.eval_every
         best = model.train(a.epochs or 2, a.batchsize or 128)
-        model.save_model()
+        if rank == 0:
+            model.save_model()
     elif a.dataset == "xlong":                                  # hpmn.py:627-664
         pv_cnt = 19002
         if a.synthetic:
@@ -81,15 +91,17 @@ def main(argv=None):
         feature_size = pv_cnt + graph_rows + 20000
         model = Hpmn_Industry(os.path.join(a.out, "xlong/hpmn/"), train_set, test_set, feature_size, 2, 1, 1000 + 1, 184,
                               0.001, 32, 16, 3, [2] * 10 + [1], [3, 2, 2, 2, 2, 2, 2, 1], 5, 8, True, False,
-                              emb_initializer, l2_reg=0, memory_reg=5e-5, max_batch=2048)
+                              emb_initializer, l2_reg=0, memory_reg=5e-5, max_batch=2048, **dev)
         if a.eval_every:
             model.eval_every = a.eval_every
         best = model.train(epochs=a.epochs or 3, batchsize=a.batchsize or 500)
-        model.get_weights()
+        if rank == 0:
+            model.get_weights()
     else:
         print("Dataset must be one of taobao or amazon.")       # sic, hpmn.py:666
         return 1
-    print("best test AUC: %.5f" % best)
+    if rank == 0:
+        print("best test AUC: %.5f" % best)
     return 0
 
 

@@ -72,6 +72,8 @@ SYMBOLS = {
     "hpmn_prefetch_host": (_I, [_P, _SH, _P, _P, _P]),
     "hpmn_clip_adam": (_I, [_P, _P, _P, _P, _P, _L, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "hpmn_debug_wgrad": (_I, [_P, _SH, _I, _P, _L, _P, _P, _P, _I, _P]),
+    "hpmn_nvls_allreduce": (_I, [_P, _P, _L, _I, _I, _I, _P]),
+    "hpmn_table_grad_sources": (_I, [_P, _SH, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hpmn_debug_tcr_stamps": (_I, [C.POINTER(C.c_longlong), _I]),
     "hpmn_profile_enable": (_I, [_P, _I]),
     "hpmn_profile_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_L)]),

@@ -916,6 +916,32 @@ int hpmn_debug_wgrad(hpmn_ctx* ctx, const hpmn_shape* s, int k, const float* xin
   return check_launch(ctx, "hpmn_debug_wgrad");
 }
 
+int hpmn_nvls_allreduce(hpmn_ctx* ctx, float* multicast_ptr, int64_t n_floats, int rank, int world, int ctas, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  if (!multicast_ptr || n_floats < 0 || (n_floats & 3) || world < 1 || rank < 0 || rank >= world)
+    return fail(ctx, HPMN_EINVAL, "bad argument (the buffer must be a multiple of 4 floats)");
+  if (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) return fail(ctx, HPMN_EINVAL, "multicast pointer must be 16-byte aligned");
+  cudaSetDevice(ctx->device);
+  Launch L{&ctx->launches, ctx->sms};
+  launch_nvls_allreduce(L, multicast_ptr, n_floats, rank, world, ctas, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_nvls_allreduce");
+}
+
+int hpmn_table_grad_sources(hpmn_ctx* ctx, const hpmn_shape* s, size_t* ids_off, size_t* dx_off, size_t* dlast_off) {
+  if (!ctx || !s || !ids_off || !dx_off || !dlast_off) return HPMN_EINVAL;
+  Dims d = make_dims(s);
+  if (!d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape");
+  int G = ctx->groups;
+  while (G > 1 && d.B / G < ctx->group_min_rows) --G;
+  if (G != 1) return fail(ctx, HPMN_EINVAL, "the step runs as %d row groups: dX is not one contiguous block", G);
+  const Hdr h = make_hdr(d);
+  const WsLayout w = make_ws_layout(d);
+  *ids_off = ctx->cur_slot ? h.ids2 : h.ids;
+  *dx_off = h.total + (want_tcrec(ctx, d) ? w.tcr + make_tcr_layout(d).dx[0] : w.dxk[0]);
+  *dlast_off = h.total + w.dlast;
+  return HPMN_OK;
+}
+
 int hpmn_debug_tcr_stamps(long long* out_host, int n) {
   long long* buf = tcr_debug_buffer();
   if (!buf || !out_host || n <= 0) return HPMN_EINVAL;

@@ -416,6 +416,9 @@ void launch_head_bwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_
                      const int32_t* labels, const float* params, const float* pred, float* drepre, float* grads,
                      const HeadWs& ws, AtbBatch& batch, cudaStream_t st);
 
+// in-switch all-reduce of a symmetric buffer through its multicast mapping (comm.cu); ctas <= 0: one CTA per SM
+void launch_nvls_allreduce(const Launch&, float* mc, int64_t n_floats, int rank, int world, int ctas, cudaStream_t st);
+
 void launch_clip_adam(const Launch&, float* var, const float* grad, float* m, float* v, int64_t n, float lr_t, float b1,
                       float b2, float eps, float clip, cudaStream_t st);
 void launch_axpy(const Launch&, float* y, const float* x, float a, int64_t n, cudaStream_t st);

@@ -72,10 +72,105 @@ def allreduce_grads(eng) -> None:
     torch.cuda.current_stream(eng.device).wait_stream(comm)
 
 
+class GradExchange:
+    """The step's gradient exchange over NVLink / NVSwitch for an HpmnEngine built with symmetric=True (csrc/comm.cu).
+
+    mode "nvls"  -- in-switch all-reduce of the flat [dense | table] gradient: rank r reduces slice r with multimem.ld_reduce
+                    and broadcasts it with multimem.st; ~|buffer| in and out per GPU whatever N (a ring moves 2(N-1)/N of it).
+    mode "rows"  -- peer-row exchange: every rank points its embedding scatter-add at each PEER's (ids, dX rows, dlast) through
+                    the symmetric mapping, so only the touched rows cross NVLink (36 MB per peer at XLong instead of the 212 MB
+                    dense table gradient) and they are added while they arrive; the 0.4 MB dense block goes through "nvls".
+    mode "nccl"  -- the flat ncclAllReduce (fallback when symmetric memory / multicast is unavailable).
+    mode "auto"  -- cost model: rows while (N-1) * (ids + rows) is less than the dense buffer, i.e. N <= 4 at XLong, else nvls.
+    Every rank must call exchange() once per step, after its backward call, on the stream that ran it."""
+
+    def __init__(self, eng, mode: str = "auto", group=None):
+        self.eng = eng
+        self.rank, self.world = rank_world()
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.mode = "nccl"
+        self.why = ""
+        self.hdl_grad = self.hdl_ws = None
+        if self.world <= 1:
+            self.mode = "none"
+            return
+        if mode == "nccl" or not getattr(eng, "symmetric", False) or eng.device.type != "cuda":
+            self.why = "engine not in symmetric memory" if mode != "nccl" else "requested"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.hdl_grad = symm_mem.rendezvous(eng.flat_grad_sym, self.group)
+            self.hdl_ws = symm_mem.rendezvous(eng.ws_sym, self.group)
+            mc = int(self.hdl_grad.multicast_ptr)
+        except Exception as e:  # noqa: BLE001 -- no symmetric memory on this system: keep the NCCL path
+            self.why = "symmetric memory unavailable: %s" % (str(e)[:120],)
+            self.hdl_grad = self.hdl_ws = None
+            return
+        self.mc_ptr = mc
+        sh = eng.shape
+        row_bytes = sh.B * sh.T * sh.F * 4 + sh.B * sh.Tpad * sh.D * 4
+        dense_bytes = eng.flat_grad_sym.numel() * 4
+        if mode == "auto":
+            mode = "rows" if (self.world - 1) * row_bytes < dense_bytes * 0.6 else "nvls"
+        if mode == "nvls" and mc == 0:
+            mode, self.why = "rows", "no multicast support"
+        if mode == "rows":
+            try:
+                eng.table_grad_sources()
+            except Exception as e:  # noqa: BLE001 -- row groups: dX is not one block
+                mode, self.why = ("nvls" if mc else "nccl"), str(e)[:120]
+        self.mode = mode
+
+    def _nvls(self, n_floats: int, offset_floats: int = 0):
+        eng = self.eng
+        _lib_check = __import__("hpmn_b200._lib", fromlist=["check"]).check
+        import ctypes as C
+        st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+        _lib_check(eng.lib.hpmn_nvls_allreduce(eng.ctx, C.c_void_p(self.mc_ptr + 4 * offset_floats), n_floats, self.rank, self.world, 0, st),
+                   eng.ctx)
+
+    def exchange(self) -> None:
+        eng = self.eng
+        if self.mode == "none":
+            return
+        if self.mode == "nccl":
+            allreduce_grads(eng)
+            return
+        if self.mode == "nvls":
+            self.hdl_grad.barrier(channel=0)                       # every rank's gradient is final
+            self._nvls(eng.flat_grad_sym.numel())
+            self.hdl_grad.barrier(channel=1)                       # every slice has been broadcast
+            return
+        # rows: dense block through the switch, table gradient by scattering the peers' rows into the local table gradient
+        import ctypes as C
+        from . import _lib
+        ids_t, B = eng.last_ids
+        ids_off, dx_off, dlast_off = eng.table_grad_sources(B)
+        ws_off = eng.workspace.storage_offset()
+        if ids_t is not None:
+            ids_off = ids_t.data_ptr() - eng.ws_sym.data_ptr()      # the device-path feed was copied into the symmetric id slot
+        cs = eng._cshape(B)
+        st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+        n_dense = (eng.n_params + 3) & ~3
+        self.hdl_ws.barrier(channel=0)                             # every rank's dX / dlast / ids and dense gradients are final
+        self._nvls(min(n_dense, eng.table_off))
+        for step in range(1, self.world):
+            peer = (self.rank + step) % self.world                 # staggered so that no two ranks read the same peer at once
+            base = int(self.hdl_ws.buffer_ptrs[peer]) + ws_off
+            _lib.check(eng.lib.hpmn_gather_bwd(eng.ctx, C.byref(cs), C.c_void_p(base + ids_off), C.c_void_p(base + dx_off),
+                                               C.c_void_p(base + dlast_off), C.c_void_p(eng.dtable.data_ptr()), st), eng.ctx)
+        self.hdl_ws.barrier(channel=1)                             # peers are done reading this rank's buffers
+
+
 def exchange_grads(eng, ids=None) -> None:
     """The step's gradient exchange for an HpmnEngine: after it every rank holds the sum over ranks of the dense gradients
-    and of the embedding-table gradient.  Default: the flat all-reduce (allreduce_grads)."""
-    allreduce_grads(eng)
+    and of the embedding-table gradient.  Uses the engine's GradExchange when one is attached (eng.exchange), else the flat
+    all-reduce (allreduce_grads)."""
+    ex = getattr(eng, "exchange", None)
+    if ex is not None:
+        ex.exchange()
+    else:
+        allreduce_grads(eng)
 
 
 def allreduce_scalars(scalars: torch.Tensor) -> torch.Tensor:

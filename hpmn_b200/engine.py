@@ -22,7 +22,9 @@ def _ptr(t: Optional[torch.Tensor]):
 class HpmnEngine:
     def __init__(self, shape: HpmnShape, device: int = 0, memory_reg: float = 1e-5, l2_reg: float = 0.0,
                  table: Optional[np.ndarray] = None, params: Optional[Dict[str, np.ndarray]] = None,
-                 seed: int = 4321):
+                 seed: int = 4321, symmetric: bool = False):
+        """symmetric: allocate the gradient buffer and the workspace in symmetric memory (torch.distributed._symmetric_memory)
+        so that peer ranks can map them -- needed by the NVLink gradient exchanges of hpmn_b200.dist.GradExchange."""
         if not torch.cuda.is_available():
             raise RuntimeError("hpmn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
@@ -46,7 +48,15 @@ class HpmnEngine:
         self.n_table = shape.V * shape.E
         self.table_off = (self.n_params + 63) & ~63
         self.flat = torch.zeros(self.table_off + self.n_table, **f32)
-        self.flat_grad = torch.zeros_like(self.flat)
+        self.symmetric = bool(symmetric)
+        n_flat = (self.flat.numel() + 3) & ~3
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.flat_grad_sym = symm_mem.empty(n_flat, dtype=torch.float32, device=self.device)
+            self.flat_grad_sym.zero_()
+            self.flat_grad = self.flat_grad_sym[: self.flat.numel()]
+        else:
+            self.flat_grad = torch.zeros_like(self.flat)
         self.comm_stream = None
         self.params = self.flat[: self.n_params]
         self.table = self.flat[self.table_off:].view(shape.V, shape.E)
@@ -59,7 +69,17 @@ class HpmnEngine:
         ws_bytes = self.lib.hpmn_workspace_bytes(C.byref(self.cshape), 1)
         if ws_bytes == 0:
             raise ValueError("invalid shape for libhpmn_b200: %r" % (shape,))
-        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            # + one id batch: the device-path feed is copied here so that peers can read it (hpmn_b200.dist.GradExchange)
+            self.ids_bytes = shape.B * shape.T * shape.F * 4
+            self.ws_sym = symm_mem.empty(((ws_bytes + 255) & ~255) + self.ids_bytes, dtype=torch.uint8, device=self.device)
+            self.workspace = self.ws_sym[:ws_bytes]
+            self.ids_sym = self.ws_sym[(ws_bytes + 255) & ~255:].view(torch.int32).view(shape.B, shape.T, shape.F)
+        else:
+            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            self.ids_sym = None
+        self.last_ids = None          # (tensor or None, rows): ids the last backward call consumed (None: the host entry point's slot)
         B, L, H = shape.B, shape.L, shape.H
         self.scalars = torch.zeros(4, **f32)
         self.pred = torch.zeros(B, **f32)
@@ -159,6 +179,10 @@ class HpmnEngine:
     def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0, seed: int = 0,
                          loss_batch: int = 0, zero_dtable: bool = True):
         hy = self._hyper(keep_prob, seed, loss_batch)
+        if self.ids_sym is not None:          # peers read this rank's ids during the peer-row exchange
+            self.ids_sym[: ids.shape[0]].copy_(ids)
+            ids = self.ids_sym[: ids.shape[0]]
+        self.last_ids = (ids, ids.shape[0])
         _lib.check(self.lib.hpmn_forward_backward(self.ctx, C.byref(self._cshape(ids.shape[0])), C.byref(hy), _ptr(ids), _ptr(labels),
                                                   _ptr(self.params), _ptr(self.table), _ptr(self.grads), _ptr(self.dtable),
                                                   int(zero_dtable), C.byref(self._out), _ptr(self.workspace),
@@ -184,6 +208,7 @@ class HpmnEngine:
         hy = self._hyper(keep_prob, seed, loss_batch)
         cs = self._cshape(B)
         st = self._stream()
+        self.last_ids = (None, B)
         _lib.check(self.lib.hpmn_step_host_begin(self.ctx, C.byref(cs), C.byref(hy), _ptr(h_ids),
                                                  _ptr(h_labels), _ptr(self.params), _ptr(self.table), _ptr(self.grads),
                                                  _ptr(self.dtable), int(zero_dtable), int(with_backward),
@@ -199,6 +224,14 @@ class HpmnEngine:
         B = self.shape.B if B is None else B
         _lib.check(self.lib.hpmn_prefetch_host(self.ctx, C.byref(self._cshape(B)), _ptr(h_ids), _ptr(h_labels),
                                                _ptr(self.workspace)), self.ctx)
+
+    def table_grad_sources(self, B: Optional[int] = None):
+        """Byte offsets inside the workspace of (id slot of the host entry point, dX of layer 0, dlast) -- what the embedding
+        scatter of the last backward call consumed (hpmn_table_grad_sources)."""
+        B = self.shape.B if B is None else B
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(self.lib.hpmn_table_grad_sources(self.ctx, C.byref(self._cshape(B)), C.byref(a), C.byref(b), C.byref(c)), self.ctx)
+        return int(a.value), int(b.value), int(c.value)
 
     def check_ids(self):
         """Device-path twin of the check hpmn_step_host_end does: forward / forward_backward embed an id outside

@@ -75,8 +75,12 @@ class Hpmn_Basic(object):
                                V=self.feature_size, front_pad=self.front_pad, mask_id0=self.mask_id0,
                                last_offset=self.last_offset)
         self.shape.steps()   # raises like TF's reshape would when a length is not divisible by its period
+        from . import dist as hd
+        world = hd.rank_world()[1]
         self.engine = HpmnEngine(self.shape, device=self._device, memory_reg=self.memory_reg, l2_reg=self.l2_reg,
-                                 table=self.emb_initializer, seed=self._seed)
+                                 table=self.emb_initializer, seed=self._seed, symmetric=world > 1)
+        if world > 1:          # torchrun: gradients are exchanged once per step over NVLink (hpmn_b200.dist.GradExchange)
+            self.engine.exchange = hd.GradExchange(self.engine)
 
     # ---- hpmn.py:91-111
     def save_model(self, global_step=None):

@@ -172,6 +172,18 @@ int hpmn_step_host_end(hpmn_ctx*, const hpmn_shape*, const hpmn_outputs* out_hos
  * current step.  The host buffers must stay untouched until the consuming call returns. */
 int hpmn_prefetch_host(hpmn_ctx*, const hpmn_shape*, const int32_t* ids_host, const int32_t* labels_host, void* workspace);
 
+/* ---- multi-GPU gradient exchange over NVLink / NVSwitch (the reference is single-process) -------- */
+/* In-switch SUM all-reduce, in place, of a buffer that lives in symmetric memory: `multicast_ptr` is the multicast address of
+ * the buffer (every rank's copy mapped behind one address), n_floats a multiple of 4.  Rank r reduces slice r with
+ * multimem.ld_reduce and broadcasts it with multimem.st.  The caller makes every rank's copy final before the launch and
+ * lets no rank read the result before every rank's launch has finished (symmetric-memory barriers on `stream`). */
+int hpmn_nvls_allreduce(hpmn_ctx*, float* multicast_ptr, int64_t n_floats, int rank, int world, int ctas, void* stream);
+/* Where, inside `workspace`, the embedding scatter of the LAST hpmn_forward_backward / hpmn_step_host call took its inputs:
+ * byte offsets of the host entry point's id slot [B,T,F] int32, of dX of layer 0 [B,Tpad,D] and of dlast [B,D].  A peer rank that
+ * maps this workspace feeds them to its own hpmn_gather_bwd (peer-row exchange: 36 MB per peer instead of the dense table
+ * gradient).  HPMN_EINVAL when the step ran as several row groups. */
+int hpmn_table_grad_sources(hpmn_ctx*, const hpmn_shape*, size_t* ids_off, size_t* dx_off, size_t* dlast_off);
+
 /* ---- update step: clip_by_value(g,-1,1) + dense Adam (code/hpmn.py:209-214) ---------------- */
 /* var, m, v updated in place over n floats; t = 1-based step; TF1.4 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t) */
 int hpmn_clip_adam(hpmn_ctx*, float* var, const float* grad, float* m, float* v, int64_t n, int64_t t,

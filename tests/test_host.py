@@ -64,8 +64,11 @@ def test_workspace_and_shape_validation():
     assert lib.hpmn_param_count(C.byref(bad.to_c())) < 0
     with pytest.raises(ValueError):
         bad.steps()
-    wide = layout.HpmnShape(B=4, T=20, F=2, E=16, H=64, periods=[2, 2], L=3, hops=2, V=100)    # H > 32: this build
-    assert lib.hpmn_param_count(C.byref(wide.to_c())) < 0
+    wide = layout.HpmnShape(B=4, T=20, F=2, E=16, H=64, periods=[2, 2], L=3, hops=2, V=100)    # H = 64: tensor-core recurrence
+    assert lib.hpmn_param_count(C.byref(wide.to_c())) == layout.param_layout(wide)[1]
+    assert lib.hpmn_workspace_bytes(C.byref(wide.to_c()), 1) > 0
+    odd = layout.HpmnShape(B=4, T=20, F=2, E=16, H=48, periods=[2, 2], L=3, hops=2, V=100)     # neither <= 32 nor 64
+    assert lib.hpmn_param_count(C.byref(odd.to_c())) < 0
     assert XLONG.steps() == [1024, 512, 256, 128, 64] and AMAZON.steps() == [100, 50, 25]
     assert XLONG.gru_flops_fwd_per_sample() == 24379392      # 24.38 MFLOP
 
