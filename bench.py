@@ -175,8 +175,7 @@ def run_product(args, cfg_name, cfg):
                    hops=cfg["hops"], V=cfg["V"], front_pad=cfg["front_pad"], mask_id0=cfg["mask_id0"],
                    last_offset=cfg["last_offset"])
     eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321, symmetric=world > 1)   # replicated parameters
-    exch = hd.GradExchange(eng, mode=os.environ.get("HPMN_EXCHANGE", "auto"))
-    eng.exchange = exch
+    exch = hd.GradExchange(eng, mode=os.environ.get("HPMN_EXCHANGE", "auto")).attach()
     dev = eng.device
     # NB distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
     # per-step working set is far larger than the 126 MB L2, so no explicit flush is needed

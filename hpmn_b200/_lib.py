@@ -58,6 +58,7 @@ SYMBOLS = {
     "hpmn_workspace_bytes": (C.c_size_t, [_SH, _I]),
     "hpmn_gather_fwd": (_I, [_P, _SH, _P, _P, _P, _P]),
     "hpmn_gather_bwd": (_I, [_P, _SH, _P, _P, _P, _P, _P]),
+    "hpmn_gather_bwd_multi": (_I, [_P, _SH, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "hpmn_memory_fwd": (_I, [_P, _SH, _P, _P, _P, _P, _P]),
     "hpmn_memory_bwd": (_I, [_P, _SH, _P, _P, _P, _P, _P, _P, _P]),
     "hpmn_attn_fwd": (_I, [_P, _SH, _P, _P, _P, _P, _P, _P, _P, _P]),

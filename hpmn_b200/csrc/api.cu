@@ -538,6 +538,19 @@ int hpmn_gather_bwd(hpmn_ctx* ctx, const hpmn_shape* s, const int32_t* ids, cons
   return check_launch(ctx, "hpmn_gather_bwd");
 }
 
+int hpmn_gather_bwd_multi(hpmn_ctx* ctx, const hpmn_shape* s, int nsrc, const int32_t* const* ids, const float* const* dx,
+                          const float* const* dlast, float* dtable, void* stream) {
+  if (!ctx) return HPMN_EINVAL;
+  Dims d = make_dims(s);
+  if (!d.ok) return fail(ctx, HPMN_EINVAL, "invalid hpmn_shape");
+  if (nsrc < 1 || nsrc > 64 || !ids || !dx || !dtable) return fail(ctx, HPMN_EINVAL, "bad argument");
+  for (int i = 0; i < nsrc; ++i) if (!ids[i] || !dx[i]) return fail(ctx, HPMN_EINVAL, "NULL source %d", i);
+  cudaSetDevice(ctx->device);
+  Launch L{&ctx->launches, ctx->sms};
+  launch_gather_bwd_multi(L, d, s->mask_id0 != 0, s->front_pad, s->last_offset, s->V, nsrc, ids, dx, dlast, dtable, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_gather_bwd_multi");
+}
+
 // ---- K2 / K4 ----------------------------------------------------------------------------------
 int hpmn_memory_fwd(hpmn_ctx* ctx, const hpmn_shape* s, const float* x, const float* params, float* memory,
                     void* workspace, void* stream) {

@@ -344,6 +344,11 @@ void launch_gather_fwd(const Launch&, const Dims&, bool mask_id0, int front_pad,
 void launch_gather_bwd(const Launch&, const Dims&, bool mask_id0, int front_pad, int last_offset, int64_t V,
                        const int32_t* ids, const float* dx, const float* dlast, float* dtable, cudaStream_t st);
 
+// the same scatter-add over nsrc sources in one launch (local buffers, or peer mappings: peer-row gradient exchange)
+void launch_gather_bwd_multi(const Launch&, const Dims&, bool mask_id0, int front_pad, int last_offset, int64_t V, int nsrc,
+                             const int32_t* const* ids, const float* const* dx, const float* const* dlast, float* dtable,
+                             cudaStream_t st);
+
 void launch_pack(const Launch&, const Dims&, const ParamLayout&, const PackLayout&, const float* params, float* pw,
                  cudaStream_t st);
 // C[M,N] = A[M,K](row stride lda) * W[K,N] (+ bias[N]); N, K multiples of 4

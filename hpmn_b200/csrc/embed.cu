@@ -58,11 +58,20 @@ gather_fwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ ta
   }
 }
 
+// Up to 15 sources per launch (blockIdx.y): the local (ids, dX, dlast) of the step, or -- peer-row gradient exchange, comm.cu --
+// the symmetric-memory mappings of the PEER ranks' buffers, read over NVLink as coalesced streaming loads by the very kernel
+// that adds them into the local table gradient.
+struct ScatterSources {
+  const int32_t* ids[15]; const float4* dx[15]; const float4* dlast[15];
+};
+
 template <int U, typename IdxT>
 __global__ void __launch_bounds__(256)
-gather_bwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ dx, const float4* __restrict__ dlast,
-                  float* __restrict__ dtable, int64_t total_, int T, int Tpad, int F, int E4, int front_pad,
-                  int last_tp, int mask_id0, int64_t V) {
+gather_bwd_kernel(const __grid_constant__ ScatterSources srcs, float* __restrict__ dtable, int64_t total_, int T, int Tpad, int F,
+                  int E4, int front_pad, int last_tp, int mask_id0, int64_t V) {
+  const int32_t* __restrict__ ids = srcs.ids[blockIdx.y];
+  const float4* __restrict__ dx = srcs.dx[blockIdx.y];
+  const float4* __restrict__ dlast = srcs.dlast[blockIdx.y];
   const IdxT total = (IdxT)total_;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;
   for (IdxT i0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
@@ -133,21 +142,37 @@ void launch_gather_fwd(const Launch& L, const Dims& d, bool mask_id0, int front_
   ++*L.counter;
 }
 
-void launch_gather_bwd(const Launch& L, const Dims& d, bool mask_id0, int front_pad, int last_offset, int64_t V,
-                       const int32_t* ids, const float* dx, const float* dlast, float* dtable, cudaStream_t st) {
+void launch_gather_bwd_multi(const Launch& L, const Dims& d, bool mask_id0, int front_pad, int last_offset, int64_t V, int nsrc,
+                             const int32_t* const* ids, const float* const* dx, const float* const* dlast, float* dtable,
+                             cudaStream_t st) {
   int E4 = d.E / 4;
   int64_t total = (int64_t)d.B * d.T * d.F * E4;
   static int per_sm = 0;
   if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_bwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
     per_sm = 4;
-  int grid = grid_for(total, 256 * 4, L.sms, per_sm);
-  if ((int64_t)d.B * d.Tpad * d.F * E4 < (int64_t)1 << 31)
-    gather_bwd_kernel<4, uint32_t><<<grid, 256, 0, st>>>(ids, (const float4*)dx, (const float4*)dlast, dtable, total, d.T, d.Tpad,
-                                                         d.F, E4, front_pad, d.Tpad - last_offset, mask_id0 ? 1 : 0, V);
-  else
-    gather_bwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(ids, (const float4*)dx, (const float4*)dlast, dtable, total, d.T, d.Tpad,
-                                                        d.F, E4, front_pad, d.Tpad - last_offset, mask_id0 ? 1 : 0, V);
-  ++*L.counter;
+  for (int s0 = 0; s0 < nsrc; s0 += 15) {
+    const int n = nsrc - s0 < 15 ? nsrc - s0 : 15;
+    ScatterSources S; memset(&S, 0, sizeof(S));
+    for (int i = 0; i < n; ++i) {
+      S.ids[i] = ids[s0 + i]; S.dx[i] = reinterpret_cast<const float4*>(dx[s0 + i]);
+      S.dlast[i] = reinterpret_cast<const float4*>(dlast ? dlast[s0 + i] : nullptr);
+    }
+    // all sources share the machine: the grid of one source is sized for 1/n of the resident blocks (at least one per SM)
+    int share = per_sm / n; if (share < 1) share = 1;
+    dim3 grid(grid_for(total, 256 * 4, L.sms, share), n);
+    if ((int64_t)d.B * d.Tpad * d.F * E4 < (int64_t)1 << 31)
+      gather_bwd_kernel<4, uint32_t><<<grid, 256, 0, st>>>(S, dtable, total, d.T, d.Tpad, d.F, E4, front_pad, d.Tpad - last_offset,
+                                                           mask_id0 ? 1 : 0, V);
+    else
+      gather_bwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(S, dtable, total, d.T, d.Tpad, d.F, E4, front_pad, d.Tpad - last_offset,
+                                                          mask_id0 ? 1 : 0, V);
+    ++*L.counter;
+  }
+}
+
+void launch_gather_bwd(const Launch& L, const Dims& d, bool mask_id0, int front_pad, int last_offset, int64_t V,
+                       const int32_t* ids, const float* dx, const float* dlast, float* dtable, cudaStream_t st) {
+  launch_gather_bwd_multi(L, d, mask_id0, front_pad, last_offset, V, 1, &ids, &dx, dlast ? &dlast : nullptr, dtable, st);
 }
 
 }  // namespace hpmn

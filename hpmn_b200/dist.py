@@ -81,7 +81,8 @@ class GradExchange:
                     the symmetric mapping, so only the touched rows cross NVLink (36 MB per peer at XLong instead of the 212 MB
                     dense table gradient) and they are added while they arrive; the 0.4 MB dense block goes through "nvls".
     mode "nccl"  -- the flat ncclAllReduce (fallback when symmetric memory / multicast is unavailable).
-    mode "auto"  -- cost model: rows while (N-1) * (ids + rows) is less than the dense buffer, i.e. N <= 4 at XLong, else nvls.
+    mode "auto"  -- cost model: rows while (N-1) * (ids + rows) < 1.3 x the dense buffer (measured on 8 x B200, XLong: rows move
+                    249 MB per GPU in 0.47 ms, the in-switch all-reduce 212 MB in 0.55 ms, ncclAllReduce 0.60 ms), else nvls.
     Every rank must call exchange() once per step, after its backward call, on the stream that ran it."""
 
     def __init__(self, eng, mode: str = "auto", group=None):
@@ -111,7 +112,7 @@ class GradExchange:
         row_bytes = sh.B * sh.T * sh.F * 4 + sh.B * sh.Tpad * sh.D * 4
         dense_bytes = eng.flat_grad_sym.numel() * 4
         if mode == "auto":
-            mode = "rows" if (self.world - 1) * row_bytes < dense_bytes * 0.6 else "nvls"
+            mode = "rows" if (self.world - 1) * row_bytes < dense_bytes * 1.3 else "nvls"
         if mode == "nvls" and mc == 0:
             mode, self.why = "rows", "no multicast support"
         if mode == "rows":
@@ -126,8 +127,18 @@ class GradExchange:
         _lib_check = __import__("hpmn_b200._lib", fromlist=["check"]).check
         import ctypes as C
         st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
-        _lib_check(eng.lib.hpmn_nvls_allreduce(eng.ctx, C.c_void_p(self.mc_ptr + 4 * offset_floats), n_floats, self.rank, self.world, 0, st),
+        ctas = int(os.environ.get("HPMN_NVLS_CTAS", "0"))
+        _lib_check(eng.lib.hpmn_nvls_allreduce(eng.ctx, C.c_void_p(self.mc_ptr + 4 * offset_floats), n_floats, self.rank, self.world, ctas, st),
                    eng.ctx)
+
+    def attach(self) -> "GradExchange":
+        """Overlap: the table part of the exchange runs on its own stream, which the library releases as soon as the local
+        scatter-add is done (hpmn_set_comm_stream) -- i.e. beside the GRU weight-gradient reduction that ends the backward call."""
+        if self.mode in ("nvls", "rows") and os.environ.get("HPMN_EXCHANGE_OVERLAP", "1") != "0":
+            self.comm = torch.cuda.Stream(device=self.eng.device)
+            self.eng.set_comm_stream(self.comm)
+        self.eng.exchange = self
+        return self
 
     def exchange(self) -> None:
         eng = self.eng
@@ -136,30 +147,39 @@ class GradExchange:
         if self.mode == "nccl":
             allreduce_grads(eng)
             return
-        if self.mode == "nvls":
-            self.hdl_grad.barrier(channel=0)                       # every rank's gradient is final
-            self._nvls(eng.flat_grad_sym.numel())
-            self.hdl_grad.barrier(channel=1)                       # every slice has been broadcast
-            return
-        # rows: dense block through the switch, table gradient by scattering the peers' rows into the local table gradient
         import ctypes as C
         from . import _lib
-        ids_t, B = eng.last_ids
-        ids_off, dx_off, dlast_off = eng.table_grad_sources(B)
-        ws_off = eng.workspace.storage_offset()
-        if ids_t is not None:
-            ids_off = ids_t.data_ptr() - eng.ws_sym.data_ptr()      # the device-path feed was copied into the symmetric id slot
-        cs = eng._cshape(B)
-        st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
-        n_dense = (eng.n_params + 3) & ~3
-        self.hdl_ws.barrier(channel=0)                             # every rank's dX / dlast / ids and dense gradients are final
-        self._nvls(min(n_dense, eng.table_off))
-        for step in range(1, self.world):
-            peer = (self.rank + step) % self.world                 # staggered so that no two ranks read the same peer at once
-            base = int(self.hdl_ws.buffer_ptrs[peer]) + ws_off
-            _lib.check(eng.lib.hpmn_gather_bwd(eng.ctx, C.byref(cs), C.c_void_p(base + ids_off), C.c_void_p(base + dx_off),
-                                               C.c_void_p(base + dlast_off), C.c_void_p(eng.dtable.data_ptr()), st), eng.ctx)
-        self.hdl_ws.barrier(channel=1)                             # peers are done reading this rank's buffers
+        main = torch.cuda.current_stream(eng.device)
+        comm = getattr(self, "comm", None)
+        n_dense = min((eng.n_params + 3) & ~3, eng.table_off)
+        n_all = eng.flat_grad_sym.numel()
+        if self.mode == "rows":
+            ids_t, B = eng.last_ids
+            ids_off, dx_off, dlast_off = eng.table_grad_sources(B)
+            if ids_t is not None:
+                ids_off = ids_t.data_ptr() - eng.ws_sym.data_ptr()  # the device-path feed was copied into the symmetric id slot
+            cs = eng._cshape(B)
+        # ---- table gradient: on the comm stream (released by the library behind the local scatter) when attached, else in line
+        with torch.cuda.stream(comm if comm is not None else main):
+            self.hdl_ws.barrier(channel=0)                         # every rank's table gradient / dX rows / ids are final
+            if self.mode == "nvls":
+                self._nvls(n_all - eng.table_off, eng.table_off)
+            else:
+                st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+                n = self.world - 1
+                peers = [(self.rank + k) % self.world for k in range(1, self.world)]     # staggered start per rank
+                bases = [int(self.hdl_ws.buffer_ptrs[p]) for p in peers]
+                arr = C.c_void_p * n
+                _lib.check(eng.lib.hpmn_gather_bwd_multi(eng.ctx, C.byref(cs), n, arr(*[b + ids_off for b in bases]),
+                                                         arr(*[b + dx_off for b in bases]), arr(*[b + dlast_off for b in bases]),
+                                                         C.c_void_p(eng.dtable.data_ptr()), st), eng.ctx)
+            if comm is not None:
+                comm.wait_stream(main)                             # the dense gradients are final at the end of the backward call
+            self.hdl_ws.barrier(channel=1)                         # ... on every rank; and every rank is done reading peers' rows
+            self._nvls(n_dense)
+            self.hdl_ws.barrier(channel=2)                         # every slice of the dense block has been broadcast
+        if comm is not None:
+            main.wait_stream(comm)
 
 
 def exchange_grads(eng, ids=None) -> None:

@@ -80,7 +80,7 @@ class Hpmn_Basic(object):
         self.engine = HpmnEngine(self.shape, device=self._device, memory_reg=self.memory_reg, l2_reg=self.l2_reg,
                                  table=self.emb_initializer, seed=self._seed, symmetric=world > 1)
         if world > 1:          # torchrun: gradients are exchanged once per step over NVLink (hpmn_b200.dist.GradExchange)
-            self.engine.exchange = hd.GradExchange(self.engine)
+            hd.GradExchange(self.engine).attach()
 
     # ---- hpmn.py:91-111
     def save_model(self, global_step=None):

@@ -104,6 +104,11 @@ int hpmn_gather_fwd(hpmn_ctx*, const hpmn_shape*, const int32_t* ids, const floa
 int hpmn_gather_bwd(hpmn_ctx*, const hpmn_shape*, const int32_t* ids, const float* dx,
                     const float* dlast, float* dtable, void* stream);
 
+/* the same adjoint over nsrc (<= 64) sources in one launch: ids[i], dx[i], dlast[i] (dlast may be NULL) are device pointers --
+ * this rank's own buffers or the symmetric-memory mappings of peer ranks' buffers (peer-row gradient exchange, see below) */
+int hpmn_gather_bwd_multi(hpmn_ctx*, const hpmn_shape*, int nsrc, const int32_t* const* ids, const float* const* dx,
+                          const float* const* dlast, float* dtable, void* stream);
+
 /* ---- K2 / K4: hierarchical periodic memory (code/hpmn.py:113-131; cell code/util.py:81-110) -- */
 /* x [B,Tpad,D], params flat -> memory [B,L,H]; activations for the adjoint are kept in workspace */
 int hpmn_memory_fwd(hpmn_ctx*, const hpmn_shape*, const float* x, const float* params, float* memory,

@@ -31,8 +31,7 @@ def main():
     ok = True
     for mode in ("nccl", "nvls", "rows", "auto"):
         eng = HpmnEngine(sh.with_batch(hi - lo), device=local_rank, memory_reg=1e-3, table=table, params=params, symmetric=True)
-        ex = hd.GradExchange(eng, mode=mode)
-        eng.exchange = ex
+        ex = hd.GradExchange(eng, mode=mode).attach()
         d_ids, d_lab = torch.as_tensor(ids[lo:hi], device=dev), torch.as_tensor(labels[lo:hi], device=dev)
         errs = []
         for it in range(3):                    # repeated steps: the barriers must also order step i+1 against step i
