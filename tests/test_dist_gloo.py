@@ -48,6 +48,13 @@ def _worker(rank, world, port, B, q):
     eng = _Eng(); eng.flat_grad = torch.from_numpy(_flat(g, dtb)).clone(); eng.comm_stream = None
     hd.allreduce_grads(eng)
     assert torch.equal(eng.flat_grad, flat)
+    # GradExchange on an engine that is not in symmetric memory (CPU / gloo here) must fall back to the flat all-reduce
+    eng2 = _Eng(); eng2.flat_grad = torch.from_numpy(_flat(g, dtb)).clone(); eng2.comm_stream = None
+    eng2.symmetric = False; eng2.device = torch.device("cpu")
+    ex = hd.GradExchange(eng2, mode="auto").attach()
+    assert ex.mode == "nccl" and (ex.rank, ex.world) == (rank, world)
+    hd.exchange_grads(eng2)
+    assert torch.equal(eng2.flat_grad, flat)
     scal = torch.tensor([f["logloss"] * (hi - lo) / B, f["covreg"]], dtype=torch.float64)
     hd.allreduce_scalars(scal)
     hd.barrier()

@@ -586,3 +586,17 @@ def test_device_path_reports_out_of_range_id_on_check():
     with pytest.raises(_lib.HpmnError, match="feature_size"):
         eng.check_ids()
     eng.close()
+
+
+def test_multi_gpu_gradient_exchange_modes_under_torchrun():
+    """tools/dp_check.py under torchrun on every GPU of the box (>= 2): row shards + each GradExchange mode (nccl all-reduce,
+    in-switch multimem all-reduce, peer-row scatter through symmetric memory) must reproduce the single-GPU gradient."""
+    import subprocess, sys, torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (host logic covered on CPU by tests/test_dist_gloo.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)), "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", "-m", "tools.dp_check"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mode rows" in r.stdout and "mode nvls" in r.stdout
