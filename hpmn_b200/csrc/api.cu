@@ -239,17 +239,20 @@ static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, cons
     if (small) launch_pack(L, d, p.pl, p.pk, params, pw, st);
   }
   auto fp = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  // H = 64: the tcgen05 weight-gradient kernel covers input widths 32 / 48; otherwise the FFMA reductions need h_prev | r*h_prev rows
+  const int dp0 = ((d.D + 15) / 16) * 16;
+  const bool need_hr = !small && !(ctx->use_tc && (dp0 == 32 || dp0 == 48));
   for (int k = d.L - 1; k >= 0; --k) {
     const float* dx_up = k < d.L - 1 ? fp(tl.dx[k + 1]) : nullptr;
     { Bracket b(ctx, st, HPMN_K_REC_BWD);
-      if (!launch_tcrec_bwd(L, d, tl, k, ws, dmemory, dx_up, !small, st)) return false; }
+      if (!launch_tcrec_bwd(L, d, tl, k, ws, dmemory, dx_up, need_hr, st)) return false; }
     { Bracket b(ctx, st, HPMN_K_DX);
       float* dxk = k == 0 ? dx0 : fp(tl.dx[k]);
       const int64_t rows = (int64_t)d.B * d.S[k];
       if (small) {
         dense_gemm(ctx, L, fp(tl.da[k]), G3, pw + p.pk.WxT[k], nullptr, dxk, rows, d.DinP[k], G3, st);
-      } else {
-        // dX[rows, Din] = da[rows, 3H] * [Wg_x | Wc_x]^T : two FFMA GEMMs against the TF-layout kernels (x rows), accumulated
+      } else if (!(ctx->use_tc && launch_tc_gemm_nn(L, fp(tl.da[k]), 3 * H, fp(tl.wxt[k]), nullptr, dxk, rows, d.Din[k], 3 * H, st))) {
+        // no tcgen05 instantiation for this width: two FFMA GEMMs against the x rows of the TF-layout kernels, accumulated
         launch_gemm_nt(L, fp(tl.da[k]), 3 * H, 0, params + p.pl.Wg[k], 2 * H, dxk, d.Din[k], rows, d.Din[k], 2 * H, false, st);
         launch_gemm_nt(L, fp(tl.da[k]), 3 * H, 2 * H, params + p.pl.Wc[k], H, dxk, d.Din[k], rows, d.Din[k], H, true, st);
       } }
@@ -267,23 +270,30 @@ static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, cons
     if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, st)))
       for (int k = 0; k < d.L; ++k) launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], st);
   } else {
-    // [x | h_prev]^T da_g, [x | r*h_prev]^T da_c, column sums: batched A^T B reductions (FFMA) over the rows of every layer
-    AtbBatch batch; batch.n = 0; batch.blocks = 0;
+    const float* xa[HPMN_MAX_LAYERS]; int64_t lx[HPMN_MAX_LAYERS]; const float* stp[HPMN_MAX_LAYERS]; const float* dap[HPMN_MAX_LAYERS];
+    float *gWg[HPMN_MAX_LAYERS], *gbg[HPMN_MAX_LAYERS], *gWc[HPMN_MAX_LAYERS], *gbc[HPMN_MAX_LAYERS];
     for (int k = 0; k < d.L; ++k) {
-      const int64_t rows = (int64_t)d.B * d.S[k];
-      const float* xin = k == 0 ? x : fp(tl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * 4 * H;
-      const int64_t ldx = k == 0 ? d.D : (int64_t)d.P[k - 1] * 4 * H;
-      const float* da = fp(tl.da[k]); const float* hr = fp(tl.hr[k]);
-      float* gWg = grads + p.pl.Wg[k]; float* gWc = grads + p.pl.Wc[k];
-      atb_add(batch, ctx->sms, xin, ldx, da, 3 * H, gWg, 2 * H, rows, d.Din[k], 2 * H);
-      atb_add(batch, ctx->sms, hr, 2 * H, da, 3 * H, gWg + (int64_t)d.Din[k] * 2 * H, 2 * H, rows, H, 2 * H);
-      atb_add(batch, ctx->sms, xin, ldx, da + 2 * H, 3 * H, gWc, H, rows, d.Din[k], H);
-      atb_add(batch, ctx->sms, hr + H, 2 * H, da + 2 * H, 3 * H, gWc + (int64_t)d.Din[k] * H, H, rows, H, H);
-      atb_add(batch, ctx->sms, nullptr, 0, da, 3 * H, grads + p.pl.bg[k], 2 * H, rows, 1, 2 * H);
-      atb_add(batch, ctx->sms, nullptr, 0, da + 2 * H, 3 * H, grads + p.pl.bc[k], H, rows, 1, H);
-      if (batch.n + 6 > ATB_MAX) { launch_atb_batch(L, batch, st); batch.n = 0; batch.blocks = 0; }
+      stp[k] = fp(tl.st[k]); dap[k] = fp(tl.da[k]);
+      xa[k] = k == 0 ? x : fp(tl.st[k - 1]) + (int64_t)(d.P[k - 1] - 1) * 4 * H;
+      lx[k] = k == 0 ? d.D : (int64_t)d.P[k - 1] * 4 * H;
+      gWg[k] = grads + p.pl.Wg[k]; gbg[k] = grads + p.pl.bg[k]; gWc[k] = grads + p.pl.Wc[k]; gbc[k] = grads + p.pl.bc[k];
     }
-    launch_atb_batch(L, batch, st);
+    if (!(ctx->use_tc && launch_tc_wgrad_wide(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, st))) {
+      // [x | h_prev]^T da_g, [x | r*h_prev]^T da_c, column sums: batched A^T B reductions (FFMA) over the rows of every layer
+      AtbBatch batch; batch.n = 0; batch.blocks = 0;
+      for (int k = 0; k < d.L; ++k) {
+        const int64_t rows = (int64_t)d.B * d.S[k];
+        const float* da = dap[k]; const float* hr = fp(tl.hr[k]);
+        atb_add(batch, ctx->sms, xa[k], lx[k], da, 3 * H, gWg[k], 2 * H, rows, d.Din[k], 2 * H);
+        atb_add(batch, ctx->sms, hr, 2 * H, da, 3 * H, gWg[k] + (int64_t)d.Din[k] * 2 * H, 2 * H, rows, H, 2 * H);
+        atb_add(batch, ctx->sms, xa[k], lx[k], da + 2 * H, 3 * H, gWc[k], H, rows, d.Din[k], H);
+        atb_add(batch, ctx->sms, hr + H, 2 * H, da + 2 * H, 3 * H, gWc[k] + (int64_t)d.Din[k] * H, H, rows, H, H);
+        atb_add(batch, ctx->sms, nullptr, 0, da, 3 * H, gbg[k], 2 * H, rows, 1, 2 * H);
+        atb_add(batch, ctx->sms, nullptr, 0, da + 2 * H, 3 * H, gbc[k], H, rows, 1, H);
+        if (batch.n + 6 > ATB_MAX) { launch_atb_batch(L, batch, st); batch.n = 0; batch.blocks = 0; }
+      }
+      launch_atb_batch(L, batch, st);
+    }
   }
   return true;
 }

@@ -142,7 +142,8 @@ struct TcrLayout {
   size_t st[HPMN_MAX_LAYERS];                           // [B,S_k,4H] h | r | u | c
   size_t da[HPMN_MAX_LAYERS];                           // [B,S_k,3H]
   size_t dx[HPMN_MAX_LAYERS];                           // [B,S_k,DP]
-  size_t hr[HPMN_MAX_LAYERS];                           // [B,S_k,2H] h_prev | r*h_prev (weight-gradient operands)
+  size_t hr[HPMN_MAX_LAYERS];                           // [B,S_k,2H] h_prev | r*h_prev (operands of the FFMA weight-gradient fallback)
+  size_t wxt[HPMN_MAX_LAYERS];                          // [3H][Din_k] = [Wg_x | Wc_x]^T (dX = dA * WxT), fp32
   size_t total;
 };
 struct Dims;
@@ -261,6 +262,14 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
+// same with a 64-byte L2 fill: a 64-byte embedding row that misses must not drag its 128-byte line partner in from DRAM
+// (ncu r1: 83 MB read for 36 MB of rows)
+__device__ __forceinline__ float4 ldg_nc_f4_l2_64(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -367,6 +376,10 @@ bool launch_tc_wgrad(const Launch&, const Dims&, int k, const float* xin, int64_
 bool launch_tc_wgrad_all(const Launch&, const Dims&, const float* const* xin, const int64_t* ldx, const float* const* st,
                          const float* const* da, float* const* dWg, float* const* dbg, float* const* dWc, float* const* dbc,
                          cudaStream_t st_);
+// H = 64 with the row layouts of tcrec.cu (state rows 4 x 64, dA rows 3 x 64): the same kernel over 32 x 32 slices
+bool launch_tc_wgrad_wide(const Launch&, const Dims&, const float* const* xin, const int64_t* ldx, const float* const* st,
+                          const float* const* da, float* const* dWg, float* const* dbg, float* const* dWc, float* const* dbc,
+                          cudaStream_t st_);
 // batched C[I,N](ldc) += sum_m A[m,I](lda) * Bm[m,N](ldb) with atomic accumulation; A == nullptr -> ones
 struct AtbProb {
   const float* A; const float* Bm; float* C;

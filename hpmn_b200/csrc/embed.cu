@@ -5,6 +5,8 @@
 // HBM-bound.  A row is E floats (64 B at E=16): E/4 lanes move one row with 128-bit accesses, so a
 // warp reads 8 random rows and writes 512 contiguous bytes of x.  Each thread keeps 4 independent row
 // loads in flight (grid-stride, unrolled) and the grid is a multiple of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hpmn {
@@ -17,7 +19,7 @@ template <int U, typename IdxT>
 __global__ void __launch_bounds__(256)
 gather_fwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ table, float4* __restrict__ x,
                   int64_t total_, int T, int Tpad, int F, int E4, int front_pad, int mask_id0, int64_t V,
-                  float* __restrict__ iderr) {
+                  float* __restrict__ iderr, int l2_64) {
   const IdxT total = (IdxT)total_;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;
   for (IdxT i0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
@@ -47,7 +49,8 @@ gather_fwd_kernel(const int32_t* __restrict__ ids, const float4* __restrict__ ta
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool oob = id[u] < 0 || (int64_t)id[u] >= V;
       bad |= live[u] && oob;
-      if (live[u] && !oob && !(mask_id0 && id[u] == 0)) v[u] = ldg_nc_f4(table + (int64_t)id[u] * E4 + q[u]);
+      if (live[u] && !oob && !(mask_id0 && id[u] == 0))
+        v[u] = l2_64 ? ldg_nc_f4_l2_64(table + (int64_t)id[u] * E4 + q[u]) : ldg_nc_f4(table + (int64_t)id[u] * E4 + q[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -133,12 +136,15 @@ void launch_gather_fwd(const Launch& L, const Dims& d, bool mask_id0, int front_
   if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_fwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
     per_sm = 4;
   int grid = grid_for(total, 256 * 4, L.sms, per_sm);
+  // rows of at most 64 bytes: ask L2 for 64-byte fills (HPMN_GATHER_L2_64=0 restores the default 128-byte granularity)
+  static const int l2_64_env = [] { const char* e = getenv("HPMN_GATHER_L2_64"); return e ? atoi(e) : 1; }();
+  const int l2_64 = (l2_64_env && d.E * 4 <= 64) ? 1 : 0;
   if (total < (int64_t)1 << 31)
     gather_fwd_kernel<4, uint32_t><<<grid, 256, 0, st>>>(ids, (const float4*)table, (float4*)x, total, d.T, d.Tpad, d.F, E4,
-                                                         front_pad, mask_id0 ? 1 : 0, V, iderr);
+                                                         front_pad, mask_id0 ? 1 : 0, V, iderr, l2_64);
   else
     gather_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(ids, (const float4*)table, (float4*)x, total, d.T, d.Tpad, d.F, E4,
-                                                        front_pad, mask_id0 ? 1 : 0, V, iderr);
+                                                        front_pad, mask_id0 ? 1 : 0, V, iderr, l2_64);
   ++*L.counter;
 }
 

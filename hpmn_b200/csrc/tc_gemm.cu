@@ -247,11 +247,18 @@ __device__ __forceinline__ void put_t(unsigned char* hi_base, unsigned char* lo_
 constexpr int WPW = 8;                 // producer warps (2 per SM sub-partition: the convert/transposing stores are issue-bound)
 
 // one launch serves every layer that shares the padded input width: CTA -> (layer, row range)
+// H <= 32: one problem per layer.  H = 64 (tensor-core recurrence, tcrec.cu): four sub-problems per layer -- hidden rows
+// [32a, 32a+32) of h_prev / r*h_prev against gate columns [32b, 32b+32) of r, u, c -- each with the same 128 x 96 tile shape;
+// the x rows and the bias row are taken from a = 0 only.
 struct WgradProb {
   const float* xin; const float* st; const float* da;
   float* dWg; float* dbg; float* dWc; float* dbc;
   int64_t ldx, M, rows_per_cta;
-  int S, Din, cta_begin, pad_;
+  int S, Din, cta_begin, hrow0;        // Din: x rows of this problem's tile; hrow0: first h row of the TF kernel (the layer's real Din)
+  int use_x, use_h, use_bias, pad_;    // which row groups of the tile this problem contributes
+  int st_stride, h_off, r_off;         // floats: state row stride (4 Htot), offset of the h / r slice inside a row
+  int da_stride, da_gate, da_off;      // floats: dA row stride (3 Htot), stride between gates (Htot), offset of the slice inside a gate
+  int Htot, Hsub;                      // hidden size of the layer, width of this slice (<= 32)
 };
 struct WgradBatch { int n, H, producer_fence, pad_; WgradProb p[HPMN_MAX_LAYERS]; };
 
@@ -265,7 +272,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   const float* __restrict__ xin = P.xin; const float* __restrict__ st = P.st; const float* __restrict__ da = P.da;
   float* __restrict__ dWg = P.dWg; float* __restrict__ dbg = P.dbg; float* __restrict__ dWc = P.dWc; float* __restrict__ dbc = P.dbc;
   const int64_t ldx = P.ldx, M = P.M, rows_per_cta = P.rows_per_cta;
-  const int S = P.S, Din = P.Din, H = batch.H;
+  const int S = P.S, Din = P.Din, H = P.Hsub, Htot = P.Htot;
   const int cta = (int)blockIdx.x - P.cta_begin;
   constexpr int XC = DINP / 4;           // feature chunks of x
   constexpr int NXU = XC;                // work units (16 rows x 2 chunks) in the x part
@@ -318,9 +325,13 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
     const float4* px[NX]; const float4* pd[3];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { const int u = warp + WPW * i; px[i] = reinterpret_cast<const float4*>(xin + (mbeg + rrow) * ldx) + 2 * (u >> 1) + lc; }
-    const float4* ph = reinterpret_cast<const float4*>(st + (mbeg + rrow) * ST) + 2 * (warp >> 1) + lc;   // row m; h_prev is one row up
+    const int sst4 = P.st_stride / 4, sda4 = P.da_stride / 4, r_rel4 = (P.r_off - P.h_off) / 4;
+    const float4* ph = reinterpret_cast<const float4*>(st + (mbeg + rrow) * P.st_stride + P.h_off) + 2 * (warp >> 1) + lc;   // row m; h_prev is one row up
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { const int u = warp + WPW * i; pd[i] = reinterpret_cast<const float4*>(da + (mbeg + rrow) * G3) + 2 * (u >> 1) + lc; }
+    for (int i = 0; i < 3; ++i) {       // 16-byte chunk c of the [r | u | c] slice: gate c / 8, chunk c % 8 inside the gate
+      const int u = warp + WPW * i, c = 2 * (u >> 1) + lc;
+      pd[i] = reinterpret_cast<const float4*>(da + (mbeg + rrow) * P.da_stride + (c >> 3) * P.da_gate + P.da_off) + (c & 7);
+    }
     const int64_t sx = (int64_t)WK * ldx / 4;                // float4 strides of one stage
     auto load = [&](Regs& R, int) {
       const bool ok = rrow < nrows;
@@ -331,13 +342,13 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
         R.x[i] = (ok && u < NXU) ? __ldg(px[i]) : z;
         px[i] += sx;
       }
-      R.h[0] = (ok && hrem != 0) ? __ldg(ph - ST / 4) : z;
-      R.r[0] = ok ? __ldg(ph + HP / 4) : z;
-      ph += WK * ST / 4;
+      R.h[0] = (ok && hrem != 0) ? __ldg(ph - sst4) : z;
+      R.r[0] = ok ? __ldg(ph + r_rel4) : z;
+      ph += WK * sst4;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         R.d[i] = ok ? __ldg(pd[i]) : z;
-        pd[i] += WK * G3 / 4;
+        pd[i] += WK * sda4;
       }
       rrow += WK;
       hrem += WK;
@@ -393,10 +404,10 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
     tc_fence_after();
     const int i = warp * 32 + lane;
     int kind, row;                       // kind 0: x row, 1: h row (gates only), 2: r*h row (candidate only), 3: bias, -1: pad
-    if (i < DINP) { kind = i < Din ? 0 : -1; row = i; }
-    else if (i < DINP + 32) { kind = (i - DINP) < H ? 1 : -1; row = Din + (i - DINP); }
-    else if (i < DINP + 64) { kind = (i - DINP - 32) < H ? 2 : -1; row = Din + (i - DINP - 32); }
-    else { kind = i == 127 ? 3 : -1; row = 0; }
+    if (i < DINP) { kind = (i < Din && P.use_x) ? 0 : -1; row = i; }
+    else if (i < DINP + 32) { kind = ((i - DINP) < H && P.use_h) ? 1 : -1; row = P.hrow0 + P.h_off + (i - DINP); }
+    else if (i < DINP + 64) { kind = ((i - DINP - 32) < H && P.use_h) ? 2 : -1; row = P.hrow0 + P.h_off + (i - DINP - 32); }
+    else { kind = (i == 127 && P.use_bias) ? 3 : -1; row = 0; }
 #pragma unroll
     for (int cb = 0; cb < 6; ++cb) {
       float v[16];
@@ -407,12 +418,13 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
       for (int q = 0; q < 16; ++q) {
         const int j = (cb & 1) * 16 + q;
         if (j >= H) continue;
+        const int col = P.da_off + j;                                    // column inside the gate
         if (kind == 3) {
-          if (g < 2) atomicAdd(dbg + g * H + j, v[q]); else atomicAdd(dbc + j, v[q]);
+          if (g < 2) atomicAdd(dbg + g * Htot + col, v[q]); else atomicAdd(dbc + col, v[q]);
         } else if (g < 2) {
-          if (kind != 2) atomicAdd(dWg + (int64_t)row * 2 * H + g * H + j, v[q]);
+          if (kind != 2) atomicAdd(dWg + (int64_t)row * 2 * Htot + g * Htot + col, v[q]);
         } else {
-          if (kind != 1) atomicAdd(dWc + (int64_t)row * H + j, v[q]);
+          if (kind != 1) atomicAdd(dWc + (int64_t)row * Htot + col, v[q]);
         }
       }
     }
@@ -450,9 +462,18 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
 static int wgrad_producer_fence() { static int v = -1; if (v < 0) { const char* e = getenv("HPMN_WGRAD_FENCE"); v = (e && e[0] == '1') ? 1 : 0; } return v; }
 
 static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin, int64_t ldx, const float* st, const float* da,
-                            float* dWg, float* dbg, float* dWc, float* dbc, int64_t M, int S, int Din, int64_t total_rows) {
+                            float* dWg, float* dbg, float* dWc, float* dbc, int64_t M, int S, int Din, int64_t total_rows,
+                            int Htot = 0, int a = 0, int bq = 0) {
   WgradProb& P = b.p[b.n++];
   P.xin = xin; P.st = st; P.da = da; P.dWg = dWg; P.dbg = dbg; P.dWc = dWc; P.dbc = dbc; P.ldx = ldx; P.M = M; P.S = S; P.Din = Din;
+  P.hrow0 = Din; P.use_x = P.use_h = P.use_bias = 1; P.pad_ = 0;
+  if (Htot <= HP) {                      // wavefront / per-layer layout: rows padded to 32 lanes, H real columns
+    P.Htot = Htot > 0 ? Htot : b.H; P.Hsub = P.Htot; P.st_stride = ST; P.h_off = 0; P.r_off = HP; P.da_stride = G3; P.da_gate = HP;
+    P.da_off = 0;
+  } else {                               // tensor-core recurrence layout: unpadded rows, slice (a, bq)
+    P.Htot = Htot; P.Hsub = 32; P.st_stride = 4 * Htot; P.h_off = 32 * a; P.r_off = Htot + 32 * a; P.da_stride = 3 * Htot;
+    P.da_gate = Htot; P.da_off = 32 * bq;
+  }
   const int64_t stages = (M + WK - 1) / WK;
   int64_t want = (int64_t)((double)sms * (double)M / (double)total_rows + 0.5);   // CTAs proportional to the layer's rows
   if (want > stages / 4) want = stages / 4;                                        // >= 4 stages per CTA
@@ -461,6 +482,53 @@ static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin,
   const int n = (int)((M + P.rows_per_cta - 1) / P.rows_per_cta);
   P.cta_begin = ctas;
   ctas += n;
+}
+
+// H = 64 (layouts of tcrec.cu: state rows [h|r|u|c] x 64, dA rows [r|u|c] x 64).  The kernel's tile is [x (32|48) | h (32) | r*h (32) |
+// ones] x [r|u|c] (3 x 32), so a layer is cut into slices: hidden rows 32a.. against gate columns 32bq..; the x rows and the bias
+// row are taken from the a = 0 slices; the layers above layer 0 have 64 input rows and get one more pair of slices for inputs [32,64).
+bool launch_tc_wgrad_wide(const Launch& L, const Dims& d, const float* const* xin, const int64_t* ldx, const float* const* st,
+                          const float* const* da, float* const* dWg, float* const* dbg, float* const* dWc, float* const* dbc,
+                          cudaStream_t st_) {
+  if (d.H != 64) return false;
+  const int dp0 = ((d.D + 15) / 16) * 16;
+  if (dp0 != 32 && dp0 != 48) return false;
+  const size_t smem = (size_t)WNS * W_STAGE + 128;
+  for (int pass = 0; pass < 2; ++pass) {          // pass 0: layer 0 (tile with 32 or 48 x rows); pass 1: the layers above (32 x rows)
+    for (int k0 = pass == 0 ? 0 : 1; k0 < (pass == 0 ? 1 : d.L); k0 += 2) {      // at most 2 layers (12 slices) per launch
+      WgradBatch b; b.n = 0; b.H = 32; b.producer_fence = wgrad_producer_fence();
+      int ctas = 0; int64_t rows = 0;
+      const int k1 = pass == 0 ? 1 : (k0 + 2 < d.L ? k0 + 2 : d.L);
+      for (int k = k0; k < k1; ++k) rows += (pass == 0 ? 4 : 6) * (int64_t)d.B * d.S[k];
+      for (int k = k0; k < k1; ++k) {
+        const int64_t M = (int64_t)d.B * d.S[k];
+        const int Dreal = d.Din[k];
+        for (int a = 0; a < 2; ++a)
+          for (int bq = 0; bq < 2; ++bq) {
+            wgrad_queue_add(b, ctas, L.sms, xin[k], ldx[k], st[k], da[k], dWg[k], dbg[k], dWc[k], dbc[k], M, d.S[k],
+                            k == 0 ? Dreal : 32, rows, 64, a, bq);
+            WgradProb& P = b.p[b.n - 1];
+            P.hrow0 = Dreal; P.use_x = a == 0; P.use_bias = a == 0;
+          }
+        if (k > 0)
+          for (int bq = 0; bq < 2; ++bq) {        // inputs [32,64) of the layer below: x rows only
+            wgrad_queue_add(b, ctas, L.sms, xin[k] + 32, ldx[k], st[k], da[k], dWg[k] + (int64_t)32 * 2 * 64, dbg[k],
+                            dWc[k] + (int64_t)32 * 64, dbc[k], M, d.S[k], 32, rows, 64, 0, bq);
+            WgradProb& P = b.p[b.n - 1];
+            P.hrow0 = Dreal; P.use_h = 0; P.use_bias = 0;
+          }
+      }
+      if (pass == 0 && dp0 == 48) {
+        cudaFuncSetAttribute(tc_wgrad_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_wgrad_kernel<48><<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
+      } else {
+        cudaFuncSetAttribute(tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_wgrad_kernel<32><<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
+      }
+      ++*L.counter;
+    }
+  }
+  return true;
 }
 
 bool launch_tc_wgrad_all(const Launch& L, const Dims& d, const float* const* xin, const int64_t* ldx, const float* const* st,
@@ -534,6 +602,7 @@ bool launch_tc_gemm_nn(const Launch& L, const float* A, int64_t lda, const float
 #define HPMN_TC_CASE(KK, NN) if (K == KK && N == NN) { launch_one<KK, NN>(L, A, lda, W, bias, C, M, st); return true; }
   HPMN_TC_CASE(32, 96) HPMN_TC_CASE(48, 96) HPMN_TC_CASE(64, 96)
   HPMN_TC_CASE(96, 32) HPMN_TC_CASE(96, 48) HPMN_TC_CASE(96, 64)
+  HPMN_TC_CASE(192, 32) HPMN_TC_CASE(192, 48) HPMN_TC_CASE(192, 64)          // dX at H = 64 (tensor-core recurrence)
 #undef HPMN_TC_CASE
   return false;
 }

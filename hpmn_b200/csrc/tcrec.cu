@@ -122,7 +122,7 @@ struct TcrPackArgs {
   int L, H;
   int Din[HPMN_MAX_LAYERS], DP[HPMN_MAX_LAYERS];
   int64_t Wg[HPMN_MAX_LAYERS], bg[HPMN_MAX_LAYERS], Wc[HPMN_MAX_LAYERS], bc[HPMN_MAX_LAYERS];
-  int64_t wf[HPMN_MAX_LAYERS], bf[HPMN_MAX_LAYERS], wb[HPMN_MAX_LAYERS];
+  int64_t wf[HPMN_MAX_LAYERS], bf[HPMN_MAX_LAYERS], wb[HPMN_MAX_LAYERS], wxt[HPMN_MAX_LAYERS];
 };
 
 __global__ void __launch_bounds__(256)
@@ -138,7 +138,7 @@ tcr_pack_kernel(const __grid_constant__ TcrPackArgs a, const float* __restrict__
     return g < 2 ? Wg[(int64_t)i_in * 2 * H + g * H + j] : Wc[(int64_t)i_in * H + j];
   };
   const int nf = N3 * KW;
-  const int total = nf + N3 + nf;
+  const int total = nf + N3 + nf + N3 * Din;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     if (e < nf) {                         // forward: row n, col kk
       const int n = e / KW, kk = e % KW;
@@ -153,7 +153,10 @@ tcr_pack_kernel(const __grid_constant__ TcrPackArgs a, const float* __restrict__
       pw[a.bf[k] + n] = (g < 2 ? bg[g * H + j] : bc[j]) * ((n < 2 * H) ? -tcr::LOG2E : 2.f * tcr::LOG2E);
     } else {                              // backward: rows [0,H) Wc_h^T, [H,2H) Wu_h^T, [2H,3H) Wr_h^T; K = gate column j
       const int r = e - nf - N3;
-      if (r < N3 * H) {
+      if (r >= nf) {                      // WxT [3H][Din]: dX = dA * WxT (plain fp32, split by the GEMM itself)
+        const int q = r - nf, n = q / Din, i = q % Din;
+        pw[a.wxt[k] + q] = weight(i, n);
+      } else if (r < N3 * H) {
         const int n = r / H, j = r % H, blk = n / H, i = n % H;      // output i = hidden input index
         const int col = blk == 0 ? 2 * H + j : (blk == 1 ? H + j : j);
         const float w = weight(Din + i, col);
@@ -802,6 +805,7 @@ TcrLayout make_tcr_layout(const Dims& d) {
     t.wf[k] = take(2 * nf * f);
     t.bf[k] = take((size_t)3 * H * f);
     t.wb[k] = take((size_t)2 * 3 * H * H * f);
+    t.wxt[k] = take((size_t)3 * H * d.Din[k] * f);
     t.xh[k] = take(rows * t.DP[k] * f);
     t.xl[k] = take(rows * t.DP[k] * f);
     t.st[k] = take(rows * 4 * H * f);
@@ -826,6 +830,7 @@ void launch_tcr_pack(const Launch& L, const Dims& d, const ParamLayout& pl, cons
     a.Din[k] = d.Din[k]; a.DP[k] = tl.DP[k];
     a.Wg[k] = pl.Wg[k]; a.bg[k] = pl.bg[k]; a.Wc[k] = pl.Wc[k]; a.bc[k] = pl.bc[k];
     a.wf[k] = (int64_t)(tl.wf[k] / sizeof(float)); a.bf[k] = (int64_t)(tl.bf[k] / sizeof(float)); a.wb[k] = (int64_t)(tl.wb[k] / sizeof(float));
+    a.wxt[k] = (int64_t)(tl.wxt[k] / sizeof(float));
   }
   tcr_pack_kernel<<<dim3(16, d.L), 256, 0, st>>>(a, params, reinterpret_cast<float*>(ws));
   ++*L.counter;
