@@ -101,6 +101,12 @@ __device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* tm, int c0,
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global tile store (completion tracked by the issuing thread's bulk groups); rows beyond the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -210,10 +216,13 @@ __device__ __forceinline__ float tcr_tanh_scaled(float a2) {
   return fabsf(x) < 0.15f ? small : big;
 }
 
-template <int H, int DP>
+// STG: the h|r|u|c rows leave through shared-memory staging tiles and TMA tile stores.  With lane = sample every direct store
+// instruction touches 32 different rows (32 L2 requests of 16 bytes): at 16 instructions per thread and step the LSU, not the
+// recurrence, set the step time (profiles/r2_tcrec_timeline.md).  Needs 4 x 16 KB of shared memory (H = 32).
+template <int H, int DP, bool STG>
 __global__ void __launch_bounds__(TCR_THREADS, 1)
 tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
-                 const __grid_constant__ CUtensorMap tm_w, const TcrFwdArgs a) {
+                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_st, const TcrFwdArgs a) {
   constexpr int N3 = 3 * H, KW = DP + H, NKB = KW / 32, NKX = DP / 32, NKH = H / 32;
   constexpr int WKB = N3 * 128;                      // bytes of one weight K-block tile (3H rows x 128 B)
   constexpr int HC = H / 2;                          // hidden columns per epilogue thread
@@ -231,6 +240,8 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
   unsigned char* sWh = base + 1024;                  // [NKB][3H x 128 B] hi
   unsigned char* sWl = sWh + NKB * WKB;              // lo
   unsigned char* sX = sWl + NKB * WKB;               // ring of a.nxb slots: [hi 16 KB | lo 16 KB]
+  unsigned char* sStg = sX + (size_t)a.nxb * TCR_XSLOT;   // STG: 4 staging tiles [128 rows x 128 B] (h, r, u, c), 128-byte swizzle
+  static_assert(!STG || H == 32, "staged stores: one 32-column block per gate");
   uint64_t* bar_w = bars;            // weights landed
   uint64_t* bar_r = bars + 1;        // r- and u-gate accumulators complete (h_{t-1} no longer needed as an operand)
   uint64_t* bar_2 = bars + 3;        // candidate accumulators complete
@@ -278,6 +289,25 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
       if (lane == 0) tcr::arrive(bar_h);            // "h_{-1} is in tensor memory": phase 0 of bar_h
     }
     float* strow = a.st + (live ? b : 0) * (int64_t)S * 4 * H;
+    const int srow = q * 32 + lane;                  // row of the staging tiles
+    // 16 consecutive columns of this thread's row -> staging tile of gate g (swizzled 16-byte chunks, conflict free)
+    auto stage16 = [&](int g, int col, const float (&v)[16]) {
+      unsigned char* r = sStg + g * (128 * 128) + srow * 128;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        *reinterpret_cast<float4*>(r + ((((col >> 2) + qd) ^ (srow & 7)) << 4)) = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+    };
+    // every epilogue thread has written its part of gate tiles [g0, g1): hand them to the TMA engine.  The issuing thread first
+    // waits until the engine has finished READING its earlier tiles, so that whatever is written after this barrier is free.
+    auto flush = [&](int bar_id, int g0, int g1, int t) {
+      fence_proxy_async();
+      if (tid == 0) bulk_wait_read<0>();
+      tcr::named_bar(bar_id, 32 * TCR_EPI_WARPS);
+      if (tid == 0) {
+        for (int g = g0; g < g1; ++g) tcr::tma_store_3d(&tm_st, sStg + g * (128 * 128), g * H, t, tile * 128);
+        bulk_commit();
+      }
+    };
     const int Sn = a.period > 0 ? S / a.period : 0;
     int fire = a.period;                             // steps until the next firing step
     int64_t nrow = (live ? b : 0) * (int64_t)Sn * H;
@@ -304,7 +334,9 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
         }
         tcr::st16(tl + AOFF + c0 + 16 * j, hi);
         tcr::st16(tl + AOFF + H + c0 + 16 * j, lo);
-        if (live) {
+        if (STG) {
+          stage16(1, c0 + 16 * j, v);
+        } else if (live) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(strow + H + c0 + 16 * j + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -315,6 +347,7 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
       __syncwarp();
       if (lane == 0) tcr::arrive(bar_rh);
       if (dbg) dbg[2] = clock64();
+      if (STG) flush(1, 1, 2, t);
       // ---- u gate (kept in registers) while the tensor core computes the candidate's recurrent half
       if (dbg) dbg[3] = clock64();
 #pragma unroll
@@ -323,13 +356,18 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
         tcr::ld16(acc + 1 * H + c0 + 16 * j, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) u[16 * j + i] = rcp_ftz(1.0f + ex2_ftz(v[i] + sBias[H + c0 + 16 * j + i]));
-        if (live) {
+        if (STG) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = u[16 * j + i];
+          stage16(2, c0 + 16 * j, v);
+        } else if (live) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(strow + 2 * H + c0 + 16 * j + 4 * i) =
                 make_float4(u[16 * j + 4 * i], u[16 * j + 4 * i + 1], u[16 * j + 4 * i + 2], u[16 * j + 4 * i + 3]);
         }
       }
+      if (STG) flush(2, 2, 3, t);
       // ---- candidate, blend, h' into the A operand
       if (dbg) dbg[4] = clock64();
       mbar_wait(bar_2, t & 1);
@@ -360,11 +398,14 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
           if (lane == 0) tcr::arrive(bar_h);
           if (dbg) dbg[6] = clock64();
         }
+        if (STG) { stage16(0, c0 + 16 * j, hn); stage16(3, c0 + 16 * j, v); }
         if (live) {
+          if (!STG) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            *reinterpret_cast<float4*>(strow + c0 + 16 * j + 4 * i) = make_float4(hn[4 * i], hn[4 * i + 1], hn[4 * i + 2], hn[4 * i + 3]);
-            *reinterpret_cast<float4*>(strow + 3 * H + c0 + 16 * j + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) {
+              *reinterpret_cast<float4*>(strow + c0 + 16 * j + 4 * i) = make_float4(hn[4 * i], hn[4 * i + 1], hn[4 * i + 2], hn[4 * i + 3]);
+              *reinterpret_cast<float4*>(strow + 3 * H + c0 + 16 * j + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
           }
           if (firing) {
 #pragma unroll
@@ -375,10 +416,21 @@ tcrec_fwd_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
           }
         }
       }
+      if (STG) {                                     // h tile (gate 0) and c tile (gate 3): two stores, one bulk group
+        fence_proxy_async();
+        if (tid == 0) bulk_wait_read<0>();
+        tcr::named_bar(3, 32 * TCR_EPI_WARPS);
+        if (tid == 0) {
+          tcr::tma_store_3d(&tm_st, sStg, 0, t, tile * 128);
+          tcr::tma_store_3d(&tm_st, sStg + 3 * (128 * 128), 3 * H, t, tile * 128);
+          bulk_commit();
+        }
+      }
       if (fire == 0) { fire = a.period; nrow += H; }
       strow += 4 * H;
       if (dbg) dbg[7] = clock64();
     }
+    if (STG && tid == 0) bulk_wait_read<0>();         // the staging tiles must outlive the last stores' reads
     if (live) {   // final state -> memory slot of this layer (hpmn.py:120,130)
       float* m = a.memory + (b * a.L + a.layer) * (int64_t)H + c0;
 #pragma unroll
@@ -498,9 +550,10 @@ struct TcrBwdArgs {
 
 constexpr int TCR_BSLOTS = 8;
 
-template <int H>
+template <int H, bool STG>
 __global__ void __launch_bounds__(TCR_THREADS, 1)
-tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constant__ CUtensorMap tm_w, const TcrBwdArgs a) {
+tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_da, const TcrBwdArgs a) {
   constexpr int NKH = H / 32, WKB = 3 * H * 128, HC = H / 2, BLK = 128 * 128;
   constexpr int C_DRH = 0, C_DHG = H, C_AC = 2 * H, C_AU = 4 * H, C_AR = 6 * H;     // A operands: hi [C, C+H), lo [C+H, C+2H)
   constexpr int TCOLS = 8 * H;
@@ -513,6 +566,8 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
   unsigned char* sWh = base + 1024;                  // [NKH][3H x 128 B] hi: rows [0,H) Wc_h^T, [H,2H) Wu_h^T, [2H,3H) Wr_h^T
   unsigned char* sWl = sWh + NKH * WKB;
   unsigned char* sR = sWl + NKH * WKB;               // ring of TCR_BSLOTS blocks of 16 KB
+  unsigned char* sStg = sR + (size_t)TCR_BSLOTS * BLK;   // STG: staging tiles of da_r, da_u, da_c (see tcrec_fwd_kernel)
+  static_assert(!STG || H == 32, "staged stores: one 32-column block per gate");
   uint64_t* bar_w = bars;
   uint64_t* bar_m1 = bars + 1;       // d(r*h) complete
   uint64_t* bar_m2 = bars + 2;       // dh_g complete
@@ -570,6 +625,21 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
         v[4 * qd] = f.x; v[4 * qd + 1] = f.y; v[4 * qd + 2] = f.z; v[4 * qd + 3] = f.w;
       }
     };
+    auto stage16 = [&](int g, int col, const float (&v)[16]) {
+      unsigned char* r = sStg + g * BLK + row * 128;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        *reinterpret_cast<float4*>(r + ((((col >> 2) + qd) ^ (row & 7)) << 4)) = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+    };
+    auto flush = [&](int bar_id, int g0, int g1, int t) {
+      fence_proxy_async();
+      if (tid == 0) bulk_wait_read<0>();
+      tcr::named_bar(bar_id, 32 * TCR_EPI_WARPS);
+      if (tid == 0) {
+        for (int g = g0; g < g1; ++g) tcr::tma_store_3d(&tm_da, sStg + g * BLK, g * H, t, tile * 128);
+        bulk_commit();
+      }
+    };
     auto release = [&](int idx) {                    // this warp has read everything it needs from ring block idx
       __syncwarp();
       if (lane == 0) tcr::arrive(&empty[idx % TCR_BSLOTS]);
@@ -615,7 +685,9 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
         for (int i = 0; i < 16; ++i) { hi[i] = tcr::tf32_hi(u[i]); lo[i] = tcr::tf32_lo(u[i], hi[i]); }
         tcr::st16(tl + C_AU + c0 + 16 * j, hi);
         tcr::st16(tl + C_AU + H + c0 + 16 * j, lo);
-        if (live) {
+        if (STG) {
+          stage16(2, c0 + 16 * j, dac); stage16(1, c0 + 16 * j, u);
+        } else if (live) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             *reinterpret_cast<float4*>(darow + 2 * H + c0 + 16 * j + 4 * i) = make_float4(dac[4 * i], dac[4 * i + 1], dac[4 * i + 2], dac[4 * i + 3]);
@@ -628,6 +700,7 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
       __syncwarp();
       if (lane == 0) tcr::arrive(bar_a1);
       release(i_u); release(i_c); release(i_h);
+      if (STG) flush(1, 1, 3, t);
       // ---- phase B: d(r*h) -> da_r (A operand), dh_prev += d(r*h) * r
       mbar_wait(&full[i_r % TCR_BSLOTS], par);
       mbar_wait(bar_m1, it & 1);
@@ -648,10 +721,13 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
         }
         tcr::st16(tl + C_AR + c0 + 16 * j, hi);
         tcr::st16(tl + C_AR + H + c0 + 16 * j, lo);
+        if (STG) stage16(0, c0 + 16 * j, v);
         if (live) {
+          if (!STG) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(darow + c0 + 16 * j + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(darow + c0 + 16 * j + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
           if (hrrow) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -669,6 +745,7 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
       __syncwarp();
       if (lane == 0) tcr::arrive(bar_a2);
       release(i_r);
+      if (STG) flush(2, 0, 1, t);
       // ---- phase C: dh_{t-1} = dh*u + d(r*h)*r + dh_g
       mbar_wait(bar_m2, it & 1);
       tcr::fence_after();
@@ -683,6 +760,7 @@ tcrec_bwd_kernel(const __grid_constant__ CUtensorMap tm_st, const __grid_constan
       darow -= 3 * H;
       if (hrrow) hrrow -= 2 * H;
     }
+    if (STG && tid == 0) bulk_wait_read<0>();
   } else if (warp == TCR_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -818,8 +896,8 @@ TcrLayout make_tcr_layout(const Dims& d) {
   return t;
 }
 
-static size_t tcr_fwd_smem(int H, int DP, int nxb) {
-  return 1024 + 1024 + (size_t)2 * ((DP + H) / 32) * (3 * H * 128) + (size_t)nxb * TCR_XSLOT;   // alignment slack, bias + barriers, weights, x ring
+static size_t tcr_fwd_smem(int H, int DP, int nxb, bool stg) {   // alignment slack, bias + barriers, weights, x ring, staging tiles
+  return 1024 + 1024 + (size_t)2 * ((DP + H) / 32) * (3 * H * 128) + (size_t)nxb * TCR_XSLOT + (stg ? 4 * 128 * 128 : 0);
 }
 
 void launch_tcr_pack(const Launch& L, const Dims& d, const ParamLayout& pl, const TcrLayout& tl, const float* params, char* ws,
@@ -846,16 +924,20 @@ void launch_tcr_split(const Launch& L, const float* x, float* xh, float* xl, int
 
 template <int H, int DP>
 static bool tcr_fwd_go(const Launch& L, const Dims& d, const TcrLayout& tl, int k, char* ws, float* memory, cudaStream_t st) {
-  int nxb = 4 * (DP / 32);
-  while (nxb > 1 && tcr_fwd_smem(H, DP, nxb) > 227 * 1024) --nxb;
-  if (tcr_fwd_smem(H, DP, nxb) > 227 * 1024) return false;
+  static const bool stg_env = [] { const char* e = getenv("HPMN_TCR_STAGE"); return !(e && e[0] == '0'); }();
+  constexpr bool CAN_STAGE = H == 32;
+  const bool stg = CAN_STAGE && stg_env;
+  int nxb = (stg ? 2 : 4) * (DP / 32);
+  while (nxb > 1 && tcr_fwd_smem(H, DP, nxb, stg) > 227 * 1024) --nxb;
+  if (tcr_fwd_smem(H, DP, nxb, stg) > 227 * 1024) return false;
   if (nxb > 8) nxb = 8;
-  CUtensorMap tm_xh, tm_xl, tm_w;
+  CUtensorMap tm_xh, tm_xl, tm_w, tm_st;
   const float* xh = reinterpret_cast<const float*>(ws + tl.xh[k]);
   const float* xl = reinterpret_cast<const float*>(ws + tl.xl[k]);
   if (!make_tmap(&tm_xh, xh, DP, (uint64_t)d.S[k], (uint64_t)d.B, 1, 128)) return false;
   if (!make_tmap(&tm_xl, xl, DP, (uint64_t)d.S[k], (uint64_t)d.B, 1, 128)) return false;
   if (!make_tmap(&tm_w, reinterpret_cast<const float*>(ws + tl.wf[k]), DP + H, 6 * H, 0, 3 * H, 0)) return false;
+  if (!make_tmap(&tm_st, reinterpret_cast<const float*>(ws + tl.st[k]), 4 * H, (uint64_t)d.S[k], (uint64_t)d.B, 1, 128)) return false;
   TcrFwdArgs a;
   a.bias = reinterpret_cast<const float*>(ws + tl.bf[k]);
   a.st = reinterpret_cast<float*>(ws + tl.st[k]);
@@ -866,31 +948,41 @@ static bool tcr_fwd_go(const Launch& L, const Dims& d, const TcrLayout& tl, int 
   a.B = d.B; a.S = d.S[k]; a.period = top ? 0 : d.P[k]; a.layer = k; a.L = d.L; a.nxb = nxb;
   a.dbg = k == 0 ? tcr_debug_buffer() : nullptr;
   { const char* e = getenv("HPMN_TCR_AFIRST"); a.a_first = (e && e[0] == '1') ? 1 : 0; }
-  auto kern = tcrec_fwd_kernel<H, DP>;
-  const size_t smem = tcr_fwd_smem(H, DP, nxb);
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(d.B + 127) / 128, TCR_THREADS, smem, st>>>(tm_xh, tm_xl, tm_w, a);
+  const size_t smem = tcr_fwd_smem(H, DP, nxb, stg);
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(d.B + 127) / 128, TCR_THREADS, smem, st>>>(tm_xh, tm_xl, tm_w, tm_st, a);
+  };
+  if (stg) go(tcrec_fwd_kernel<H, DP, CAN_STAGE>); else go(tcrec_fwd_kernel<H, DP, false>);
   ++*L.counter;
   return true;
 }
 
-static size_t tcr_bwd_smem(int H) { return 1024 + 1024 + (size_t)2 * (H / 32) * (3 * H * 128) + (size_t)TCR_BSLOTS * 128 * 128; }
+static size_t tcr_bwd_smem(int H, bool stg) {
+  return 1024 + 1024 + (size_t)2 * (H / 32) * (3 * H * 128) + (size_t)TCR_BSLOTS * 128 * 128 + (stg ? 3 * 128 * 128 : 0);
+}
 
 template <int H>
 static bool tcr_bwd_go(const Launch& L, const Dims& d, const TcrLayout& tl, int k, char* ws, const float* dmemory, const float* dx_up,
                        bool write_hr, cudaStream_t st) {
-  CUtensorMap tm_st, tm_w;
+  static const bool stg_env = [] { const char* e = getenv("HPMN_TCR_STAGE"); return !(e && e[0] == '0'); }();
+  constexpr bool CAN_STAGE = H == 32;
+  const bool stg = CAN_STAGE && stg_env;
+  CUtensorMap tm_st, tm_w, tm_da;
   if (!make_tmap(&tm_st, reinterpret_cast<const float*>(ws + tl.st[k]), 4 * H, (uint64_t)d.S[k], (uint64_t)d.B, 1, 128)) return false;
   if (!make_tmap(&tm_w, reinterpret_cast<const float*>(ws + tl.wb[k]), H, 6 * H, 0, 3 * H, 0)) return false;
+  if (!make_tmap(&tm_da, reinterpret_cast<const float*>(ws + tl.da[k]), 3 * H, (uint64_t)d.S[k], (uint64_t)d.B, 1, 128)) return false;
   TcrBwdArgs a;
   a.dmemory = dmemory; a.dx_up = dx_up;
   a.da = reinterpret_cast<float*>(ws + tl.da[k]);
   a.hr = write_hr ? reinterpret_cast<float*>(ws + tl.hr[k]) : nullptr;
   a.B = d.B; a.S = d.S[k]; a.period = k == d.L - 1 ? 1 : d.P[k]; a.layer = k; a.L = d.L;
-  auto kern = tcrec_bwd_kernel<H>;
-  const size_t smem = tcr_bwd_smem(H);
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(d.B + 127) / 128, TCR_THREADS, smem, st>>>(tm_st, tm_w, a);
+  const size_t smem = tcr_bwd_smem(H, stg);
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(d.B + 127) / 128, TCR_THREADS, smem, st>>>(tm_st, tm_w, tm_da, a);
+  };
+  if (stg) go(tcrec_bwd_kernel<H, CAN_STAGE>); else go(tcrec_bwd_kernel<H, false>);
   ++*L.counter;
   return true;
 }
