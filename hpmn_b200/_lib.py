@@ -65,6 +65,11 @@ SYMBOLS = {
     "hpmn_attn_bwd": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hpmn_head_fwd": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hpmn_head_bwd": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _P]),
+    "hpmn_head_wide_param_count": (_L, [_I]),
+    "hpmn_head_wide_param_offsets": (_I, [_I, C.POINTER(_L), C.POINTER(_L)]),
+    "hpmn_head_wide_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "hpmn_head_wide_fwd": (_I, [_P, _I, _I, _HY, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hpmn_head_wide_bwd": (_I, [_P, _I, _I, _HY, _P, _P, _P, _P, _P, _P, _P]),
     "hpmn_forward": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _OUT, _P, _P]),
     "hpmn_forward_backward": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _OUT, _P, _P]),
     "hpmn_step_host": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _I, _OUT, _P, _P]),

@@ -939,6 +939,74 @@ int hpmn_debug_wgrad(hpmn_ctx* ctx, const hpmn_shape* s, int k, const float* xin
   return check_launch(ctx, "hpmn_debug_wgrad");
 }
 
+// ---- head over an arbitrary input width (user + item sides concatenated, code/hpmn.py:452-465) --------------------------
+static ParamLayout head_only_layout(int R) {
+  ParamLayout p; memset(&p, 0, sizeof(p));
+  int64_t off = 0;
+  auto take = [&](int64_t sz) { int64_t o = off; off = align4(off + sz); return o; };
+  p.gamma = take(R); p.beta = take(R);
+  p.F1 = take((int64_t)R * FC1); p.f1 = take(FC1);
+  p.F2 = take((int64_t)FC1 * FC2); p.f2 = take(FC2);
+  p.F3 = take(FC2); p.f3 = take(1);
+  p.total = off; p.ntensors = 8;
+  return p;
+}
+struct HeadWideWs { HeadWs w; float* pred; size_t total; };
+static HeadWideWs head_wide_ws(char* base, int B, int R) {
+  HeadWideWs h; size_t off = 0;
+  auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(base + off); off = (off + n * sizeof(float) + 255) & ~(size_t)255; return p; };
+  h.w.bn = take((size_t)B * R); h.w.dbn = take((size_t)B * R); h.w.dgt = take((size_t)B * R);
+  h.w.a1 = take((size_t)B * FC1); h.w.act1 = take((size_t)B * FC1); h.w.dl1 = take((size_t)B * FC1);
+  h.w.a2 = take((size_t)B * FC2); h.w.act2 = take((size_t)B * FC2); h.w.dl2 = take((size_t)B * FC2);
+  h.w.dlogit = take((size_t)B); h.pred = take((size_t)B);
+  h.total = off;
+  return h;
+}
+int64_t hpmn_head_wide_param_count(int R) { return R > 0 ? head_only_layout(R).total : HPMN_EINVAL; }
+int hpmn_head_wide_param_offsets(int R, int64_t* offsets, int64_t* sizes) {
+  if (R <= 0 || !offsets || !sizes) return HPMN_EINVAL;
+  const ParamLayout p = head_only_layout(R);
+  const int64_t o[8] = {p.gamma, p.beta, p.F1, p.f1, p.F2, p.f2, p.F3, p.f3};
+  const int64_t z[8] = {R, R, (int64_t)R * FC1, FC1, (int64_t)FC1 * FC2, FC2, FC2, 1};
+  for (int i = 0; i < 8; ++i) { offsets[i] = o[i]; sizes[i] = z[i]; }
+  return 8;
+}
+size_t hpmn_head_wide_workspace_bytes(int B, int R) { return (B > 0 && R > 0) ? head_wide_ws(nullptr, B, R).total : 0; }
+
+static int head_wide_dims(hpmn_ctx* ctx, int B, int R, Dims& d) {
+  if (!ctx) return HPMN_EINVAL;
+  if (B <= 0 || R <= 0 || R > 2 * (HP + 64)) return fail(ctx, HPMN_EINVAL, "head input width %d outside (0, %d]", R, 2 * (HP + 64));
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.R = R; d.ok = true;
+  cudaSetDevice(ctx->device);
+  return HPMN_OK;
+}
+
+int hpmn_head_wide_fwd(hpmn_ctx* ctx, int B, int R, const hpmn_hyper* hy, const float* repre, const int32_t* labels, const float* hparams,
+                       float* pred, float* logit, float* scalars, void* workspace, void* stream) {
+  Dims d; int rc = head_wide_dims(ctx, B, R, d);
+  if (rc) return rc;
+  if (!hy || !repre || !labels || !hparams || !pred || !logit || !scalars || !workspace) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  HeadWideWs w = head_wide_ws(static_cast<char*>(workspace), B, R);
+  launch_head_fwd(L, d, head_only_layout(R), *hy, 0, repre, labels, hparams, w.pred, logit, scalars, w.w, (cudaStream_t)stream);
+  CK(cudaMemcpyAsync(pred, w.pred, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return check_launch(ctx, "hpmn_head_wide_fwd");
+}
+
+int hpmn_head_wide_bwd(hpmn_ctx* ctx, int B, int R, const hpmn_hyper* hy, const float* repre, const int32_t* labels, const float* hparams,
+                       float* drepre, float* hgrads, void* workspace, void* stream) {
+  Dims d; int rc = head_wide_dims(ctx, B, R, d);
+  if (rc) return rc;
+  if (!hy || !repre || !labels || !hparams || !drepre || !hgrads || !workspace) return fail(ctx, HPMN_EINVAL, "NULL buffer");
+  Launch L{&ctx->launches, ctx->sms};
+  HeadWideWs w = head_wide_ws(static_cast<char*>(workspace), B, R);
+  AtbBatch batch; batch.n = 0; batch.blocks = 0;
+  launch_head_bwd(L, d, head_only_layout(R), *hy, 0, repre, labels, hparams, w.pred, drepre, hgrads, w.w, batch, (cudaStream_t)stream);
+  launch_atb_batch(L, batch, (cudaStream_t)stream);
+  return check_launch(ctx, "hpmn_head_wide_bwd");
+}
+
 int hpmn_nvls_allreduce(hpmn_ctx* ctx, float* multicast_ptr, int64_t n_floats, int rank, int world, int ctas, void* stream) {
   if (!ctx) return HPMN_EINVAL;
   if (!multicast_ptr || n_floats < 0 || (n_floats & 3) || world < 1 || rank < 0 || rank >= world)

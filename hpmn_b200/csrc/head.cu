@@ -8,7 +8,7 @@
 
 namespace hpmn {
 
-constexpr int MR = HP + 64;   // H + F*E <= 96 in this build
+constexpr int MR = 2 * (HP + 64);   // one side: H + F*E <= 96; user + item sides concatenated (hpmn.py:452-456): <= 192
 
 struct HeadArgs {
   const float* repre; const int32_t* labels; const float* params; const float* pred_in;
@@ -163,8 +163,8 @@ head_bwd_kernel(const __grid_constant__ HeadArgs a) {
     a.ws.dl1[(int64_t)b * FC1 + tid] = d;
   }
   __syncthreads();
-  if (tid < 2 * R) {                           // row tid%R of F1 (200 floats), half of it per thread
-    const int r = tid % R, half = tid / R;
+  for (int e = tid; e < 2 * R; e += 256) {     // row e%R of F1 (200 floats), half of it per work item
+    const int r = e % R, half = e / R;
     const float4* __restrict__ row = reinterpret_cast<const float4*>(P + a.F1 + (int64_t)r * FC1) + half * (FC1 / 8);
     const float4* d4 = reinterpret_cast<const float4*>(sDl1) + half * (FC1 / 8);
     float4 w[FC1 / 8];

@@ -3,9 +3,9 @@ names, constructor signatures, methods and log / dump formats, with the TF1 sess
 HpmnEngine (libhpmn_b200.so).  `sess.run(train_step)` becomes engine.step_host + apply_gradients;
 `sess.run([memory_loss, prediction])` becomes engine.step_host(with_backward=False).
 
-Scope of this build: the `user=True, item=False` graph every reference configuration runs
-(hpmn.py:591-592, 619-620, 658-659).  The item-side memory is built by the reference but pruned at run
-time when item=False (hpmn.py:452-462); it is not instantiated here."""
+`user=True, item=False` -- the graph every reference configuration runs (hpmn.py:591-592, 619-620, 658-659) -- is the fused
+step of HpmnEngine.  `item=True` (second memory over `item_inp`, hpmn.py:444-462) runs on HpmnDualEngine, which composes both
+sides and the wider head from the K1-K5 entry points; `user=False, item=True` is the single engine over the item side."""
 from __future__ import annotations
 
 import os
@@ -27,6 +27,8 @@ def _metrics(labels, preds):
 class Hpmn_Basic(object):
     """hpmn.py:16-214.  Subclasses define the variant (front padding, id-0 mask, target position, loader)."""
 
+    item_front_pad = 0     # zero steps prepended to the item-side sequence
+    item_scope = "item"    # variable scope of the item side (hpmn.py:444; Hpmn_Industry: "Item", hpmn.py:297)
     front_pad = 0          # zero steps prepended to the user sequence
     mask_id0 = True        # embedding of id 0 forced to zeros
     last_offset = 1        # target step counted from the end
@@ -36,8 +38,8 @@ class Hpmn_Basic(object):
     def __init__(self, path, trainset, testset, feature_size, user_dim, item_dim, learning_rate, hidden_size,
                  embedding_size, hop, user_layers, item_layers, user_num_layers, item_num_layers, user, item,
                  emb_initializer=None, l2_reg=0, memory_reg=1e-5, max_batch=2048, device=0, seed=4321):
-        if not user or item:
-            raise NotImplementedError("this build implements the user=True, item=False graph the reference runs")
+        if not user and not item:
+            raise ValueError("at least one of user / item must be on (hpmn.py:452-462)")
         self._path = path
         self.trainset, self.testset = trainset, testset
         self._save_path = None
@@ -70,11 +72,25 @@ class Hpmn_Basic(object):
 
     def build_graph(self):
         """hpmn.py:432-465 / 284-320: here the "graph" is the shape handed to the engine."""
-        self.shape = HpmnShape(B=self.max_batch, T=self.user_maxlen, F=self.user_dim, E=self.embedding_size,
+        user_shape = HpmnShape(B=self.max_batch, T=self.user_maxlen, F=self.user_dim, E=self.embedding_size,
                                H=self.hidden_size, periods=list(self.user_layers), L=self.user_num_layers, hops=self.hop,
                                V=self.feature_size, front_pad=self.front_pad, mask_id0=self.mask_id0,
                                last_offset=self.last_offset)
+        # item side: its own lengths / periods, target = last step, no id-0 mask change (hpmn.py:298-304, 444-450)
+        item_shape = HpmnShape(B=self.max_batch, T=self.item_maxlen, F=self.item_dim, E=self.embedding_size,
+                               H=self.hidden_size, periods=list(self.item_layers), L=self.item_num_layers, hops=self.hop,
+                               V=self.feature_size, front_pad=self.item_front_pad, mask_id0=self.mask_id0, last_offset=1,
+                               scope=self.item_scope)
+        self.dual = bool(self.user and self.item)
+        self.shape = user_shape if self.user else item_shape
         self.shape.steps()   # raises like TF's reshape would when a length is not divisible by its period
+        if self.dual:
+            from .dual import HpmnDualEngine
+            item_shape.steps()
+            self.item_shape = item_shape
+            self.engine = HpmnDualEngine(user_shape, item_shape, device=self._device, memory_reg=self.memory_reg,
+                                         table=self.emb_initializer, seed=self._seed)
+            return
         from . import dist as hd
         world = hd.rank_world()[1]
         self.engine = HpmnEngine(self.shape, device=self._device, memory_reg=self.memory_reg, l2_reg=self.l2_reg,
@@ -90,7 +106,7 @@ class Hpmn_Basic(object):
         state = {"step": torch.tensor(eng.adam_t), "table": eng.table.cpu()}
         for name, arr in eng.named_parameters().items():
             state["param:" + name] = torch.from_numpy(arr)
-        if eng.adam_m is not None:
+        if getattr(eng, "adam_m", None) is not None:
             state["adam_m"], state["adam_v"] = eng.adam_m.cpu(), eng.adam_v.cpu()
         path = self.save_path if global_step is None else "%s-%d" % (self.save_path, global_step)
         torch.save(state, path)
@@ -102,7 +118,7 @@ class Hpmn_Basic(object):
             eng.load_named({k[6:]: v.numpy() for k, v in state.items() if k.startswith("param:")})
             eng.table.copy_(state["table"])
             eng.adam_t = int(state["step"])
-            if "adam_m" in state:
+            if "adam_m" in state and hasattr(eng, "adam_m"):
                 eng.adam_m = state["adam_m"].to(eng.device)
                 eng.adam_v = state["adam_v"].to(eng.device)
         except Exception:
@@ -118,14 +134,29 @@ class Hpmn_Basic(object):
 
     # ---- the two sess.run calls
     def _feed(self, data):
-        """feed_dict of hpmn.py:474-481: `user_inp` is fed data[1] (the item_part of the tuple)."""
-        return np.asarray(data[1], dtype=np.int32), np.asarray(data[0], dtype=np.int32)
+        """feed_dict of hpmn.py:474-481: `user_inp` is fed data[1] (the item_part of the tuple), `item_inp` data[3]."""
+        ids = data[1] if self.user else data[3]
+        return np.asarray(ids, dtype=np.int32), np.asarray(data[0], dtype=np.int32)
+
+    def _dual_feed(self, data, lo, hi):
+        dev = self.engine.device
+        return (torch.as_tensor(np.ascontiguousarray(np.asarray(data[1], dtype=np.int32)[lo:hi]), device=dev),
+                torch.as_tensor(np.ascontiguousarray(np.asarray(data[3], dtype=np.int32)[lo:hi]), device=dev),
+                torch.as_tensor(np.asarray(data[0], dtype=np.int32)[lo:hi], device=dev))
 
     def train_on_batch(self, data):
         """One `sess.run(train_step)` (hpmn.py:482).  Under torchrun (torch.distributed initialised, world > 1) the batch
         rows are sharded across the ranks, every rank back-propagates its share of the GLOBAL-batch loss, the gradients
         are exchanged once (hpmn_b200.dist.exchange_grads) and every rank applies the identical clip + Adam update."""
         from . import dist as hd
+        if self.dual:
+            if len(data[0]) > self.max_batch:
+                raise ValueError("train batch %d exceeds max_batch=%d" % (len(data[0]), self.max_batch))
+            self._step_seed += 1
+            u, i, y = self._dual_feed(data, 0, len(data[0]))
+            self.engine.forward_backward(u, i, y, keep_prob=0.5, seed=self._step_seed)
+            self.engine.apply_gradients(self.learning_rate)
+            return
         ids, labels = self._feed(data)
         n = len(labels)
         rank, world = hd.rank_world()
@@ -143,6 +174,17 @@ class Hpmn_Basic(object):
     def predict_on_batch(self, data):
         """eval fetch; batches larger than the engine capacity are evaluated in chunks (rows are independent; the
         memory loss is a sum over rows, hpmn.py:170)."""
+        if self.dual:
+            mem, preds, weights = 0.0, [], []
+            for lo in range(0, len(data[0]), self.max_batch):
+                hi = min(len(data[0]), lo + self.max_batch)
+                u, i, y = self._dual_feed(data, lo, hi)
+                self.engine.forward(u, i, y)
+                sc = self.engine.scalars.cpu().numpy()
+                mem += float(sc[1])
+                preds.append(self.engine.pred[: hi - lo].cpu().numpy())
+                weights.append(self.engine.user.w_hop0[: hi - lo].cpu().numpy())
+            return mem, np.concatenate(preds), np.concatenate(weights)
         ids, labels = self._feed(data)
         mem, preds, weights = 0.0, [], []
         for lo in range(0, len(labels), self.max_batch):
@@ -201,6 +243,8 @@ class Hpmn_Industry(Hpmn_Basic):
     XLong TSV loader, eval every 10 steps."""
 
     front_pad = 23
+    item_front_pad = 8     # 192 - 184 zero steps in front of the item side (hpmn.py:298-299)
+    item_scope = "Item"    # hpmn.py:297
     mask_id0 = False
     last_offset = 2
     eval_every = 10
@@ -235,6 +279,8 @@ class Hpmn(Hpmn_Industry):
     """hpmn.py:413-560: id-0 mask, no front padding, target = last step, in-memory loader, eval every 100 steps."""
 
     front_pad = 0
+    item_front_pad = 0
+    item_scope = "item"    # hpmn.py:444
     mask_id0 = True
     last_offset = 1
     eval_every = 100

@@ -136,6 +136,18 @@ int hpmn_head_bwd(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const float* 
                   const int32_t* labels, const float* params, float* drepre, float* grads,
                   void* workspace, void* stream);
 
+/* The same head over an arbitrary input width R <= 192: `repre = concat([user_repre, item_repre])` when both memory sides are on
+ * (item=True, code/hpmn.py:444-465).  hparams / hgrads: flat [gamma R | beta R | fc1 R x 200, 200 | fc2 200 x 80, 80 | fc3 80, 1]
+ * (every tensor on a 4-float boundary: hpmn_head_wide_param_offsets); hgrads is accumulated.  _bwd uses the activations _fwd left
+ * in `workspace` (hpmn_head_wide_workspace_bytes).  hpmn_b200/dual.py composes the two sides from the K1-K5 entry points. */
+int64_t hpmn_head_wide_param_count(int R);
+int hpmn_head_wide_param_offsets(int R, int64_t* offsets, int64_t* sizes); /* 8 tensors */
+size_t hpmn_head_wide_workspace_bytes(int B, int R);
+int hpmn_head_wide_fwd(hpmn_ctx*, int B, int R, const hpmn_hyper*, const float* repre, const int32_t* labels, const float* hparams,
+                       float* pred, float* logit, float* scalars, void* workspace, void* stream);
+int hpmn_head_wide_bwd(hpmn_ctx*, int B, int R, const hpmn_hyper*, const float* repre, const int32_t* labels, const float* hparams,
+                       float* drepre, float* hgrads, void* workspace, void* stream);
+
 /* ---- whole path: what `sess.run` does (code/hpmn.py:365-367 eval, :336/:482 train, minus Adam) */
 typedef struct hpmn_outputs {  /* each pointer may be NULL except scalars */
   float* scalars;  /* [4]  HPMN_S_* */

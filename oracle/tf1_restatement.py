@@ -26,10 +26,9 @@ def _t(p: Dict[str, np.ndarray], dtype, requires_grad=True):
     return {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=requires_grad) for k, v in p.items()}
 
 
-def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_prob=1.0, masks=None, sparse_grad=False):
-    """p: dict of torch tensors, table: torch [V,E]; ids: torch int64 [B,T,F]; labels: torch float [B].
-    sparse_grad: the table gradient is a sparse (indices, rows) tensor -- what tf.gradients returns for
-    tf.nn.embedding_lookup (IndexedSlices, before the clip of code/hpmn.py:212 densifies it)."""
+def side_torch(sh: OracleShape, p, table, ids, sparse_grad=False):
+    """One memory side (scope sh.scope) of the graph: embedding -> build_memory -> get_covreg -> query_memory
+    (hpmn.py:414-430 / 266-282, 113-131, 161-170, 172-182).  Returns x, memory, covreg, q, w_hop0, last, repre."""
     H, sc = sh.H, sh.scope
     B = ids.shape[0]
     # hpmn.py:414-430 / 266-282
@@ -87,7 +86,11 @@ def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_
         if hop == 0:
             w0 = w
     repre = torch.cat([q, last], dim=-1)
-    # hpmn.py:190-202
+    return dict(x=x, memory=memory, covreg=covreg, q=q, w_hop0=w0, last=last, repre=repre)
+
+
+def head_torch(p, repre, labels, keep_prob=1.0, masks=None):
+    """build_fc_net, hpmn.py:190-202."""
     bn = repre / float(np.sqrt(1.0 + BN_EPS)) * p["output/bn1/gamma"] + p["output/bn1/beta"]
     f1 = torch.nn.functional.elu(torch.matmul(bn, p["output/fc1/kernel"]) + p["output/fc1/bias"])
     if masks is not None:
@@ -98,8 +101,31 @@ def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_
     logit = (torch.matmul(f2, p["output/fc3/kernel"]) + p["output/fc3/bias"]).reshape(-1)
     pred = torch.sigmoid(logit)
     ll = (-labels * torch.log(pred + LOGLOSS_EPS) - (1 - labels) * torch.log(1 - pred + LOGLOSS_EPS)).mean()
+    return logit, pred, ll
+
+
+def forward_torch(sh: OracleShape, p, table, ids, labels, memory_reg=1e-5, keep_prob=1.0, masks=None, sparse_grad=False):
+    """p: dict of torch tensors, table: torch [V,E]; ids: torch int64 [B,T,F]; labels: torch float [B].
+    sparse_grad: the table gradient is a sparse (indices, rows) tensor -- what tf.gradients returns for
+    tf.nn.embedding_lookup (IndexedSlices, before the clip of code/hpmn.py:212 densifies it)."""
+    s = side_torch(sh, p, table, ids, sparse_grad)
+    logit, pred, ll = head_torch(p, s["repre"], labels, keep_prob, masks)
+    loss = ll + memory_reg * s["covreg"]
+    return dict(x=s["x"], memory=s["memory"], covreg=s["covreg"], q=s["q"], w_hop0=s["w_hop0"], logit=logit, pred=pred, logloss=ll,
+                loss=loss)
+
+
+def forward_torch_dual(sh_user: OracleShape, sh_item: OracleShape, p, table, ids_user, ids_item, labels, memory_reg=1e-5,
+                       keep_prob=1.0, masks=None):
+    """user=True, item=True (hpmn.py:432-465): both memory sides over the shared embedding table,
+    repre = concat([user_repre, item_repre]), memory_loss = umloss + imloss."""
+    u = side_torch(sh_user, p, table, ids_user)
+    i = side_torch(sh_item, p, table, ids_item)
+    repre = torch.cat([u["repre"], i["repre"]], dim=-1)
+    logit, pred, ll = head_torch(p, repre, labels, keep_prob, masks)
+    covreg = u["covreg"] + i["covreg"]
     loss = ll + memory_reg * covreg
-    return dict(x=x, memory=memory, covreg=covreg, q=q, w_hop0=w0, logit=logit, pred=pred, logloss=ll, loss=loss)
+    return dict(user=u, item=i, covreg=covreg, logit=logit, pred=pred, logloss=ll, loss=loss)
 
 
 def forward_backward_numpy(sh: OracleShape, params, table, ids, labels, memory_reg=1e-5,
