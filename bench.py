@@ -102,9 +102,9 @@ def oracle_inputs(cfg, B, seed_data=1234, seed_params=4321, V_cap=None):
 NB = 8   # distinct id batches of the product arm (rotated so that no step re-reads its ids from L2)
 
 
-def make_config(cfg_name, cfg, B, world, keep_prob):
+def make_config(cfg_name, cfg, B, world, keep_prob, ids="uniform on [1,V)"):
     """`config` of the JSON line -- identical for the product and the reference arm (same workload, same step)."""
-    return {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world,
+    return {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world, "ids": ids,
             "parallelism": "dp%d batch-sharded, replicated table, one gradient exchange per step" % world,
             "l2": "inputs larger than L2 (212 MB table + 0.56 GB streamed activations per step, %d rotating id batches)" % NB,
             "keep_prob": keep_prob, "optimizer": "excluded (fwd+bwd metric)"}
@@ -179,7 +179,8 @@ def run_product(args, cfg_name, cfg):
     dev = eng.device
     # NB distinct id batches; together with the 212 MB table and the ~0.56 GB of streamed activations the
     # per-step working set is far larger than the 126 MB L2, so no explicit flush is needed
-    h_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + 97 * rank + i)).pin_memory() for i in range(NB)]
+    h_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + 97 * rank + i, zipf=args.zipf, uid_col=args.uid_col)).pin_memory()
+             for i in range(NB)]
     h_lab = [torch.from_numpy(np.random.default_rng(99 + i + rank).integers(0, 2, size=B).astype(np.int32)).pin_memory()
              for i in range(NB)]
     d_ids = [t.to(dev) for t in h_ids]
@@ -191,22 +192,27 @@ def run_product(args, cfg_name, cfg):
         if world > 1:
             hd.exchange_grads(eng)                    # the step's gradient exchange (GradExchange: peer rows / in-switch all-reduce)
 
-    def step_host(i):
-        # the feed of step i+1 is staged on the library's copy stream while step i computes (double-buffered H2D); every
-        # step still pays its own H2D + D2H inside the timed region
-        if i == 0:
-            eng.prefetch_host(h_ids[0], h_lab[0], B)
-        eng.step_host_pinned(True, args.keep_prob, i * world + rank, loss_batch, True, B, h_ids[i % NB], h_lab[i % NB], prefetch_next=(h_ids[(i + 1) % NB], h_lab[(i + 1) % NB]))
-        if world > 1:
-            hd.exchange_grads(eng)
+    def run_host(steps):
+        # hpmn_step_host_begin / _end through HpmnEngine.step_host_stream: pinned host ids/labels in, host results out, every
+        # step pays its own H2D (staged on the library's copy stream while the previous step computes) and D2H; two steps are
+        # in flight, so the host's enqueue time of step i+1 hides behind the device time of step i
+        feeds = ((h_ids[i % NB], h_lab[i % NB]) for i in range(steps))
+        after = (lambda i: hd.exchange_grads(eng)) if world > 1 else None
+        n = 0
+        for scal, pred in eng.step_host_stream(feeds, True, args.keep_prob, seed0=1 + rank * 1000003, loss_batch=loss_batch, after_step=after):
+            n += 1
+        assert n == steps
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole=False):
         hd.barrier(); torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
-        for i in range(steps):
-            fn(i)
+        if whole:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         e1.record()
         torch.cuda.synchronize(dev); hd.barrier()
         w1 = time.time()
@@ -220,13 +226,12 @@ def run_product(args, cfg_name, cfg):
         sampler.start()          # before the warm-up: nvidia-smi needs ~0.5 s to deliver its first row, the timed regions are ~0.2 s each
     for i in range(args.warmup):
         step_dev(i)
-    for i in range(min(args.warmup, 3)):
-        step_host(i)
+    run_host(min(args.warmup, 3))
     windows = []
     l0 = eng.launch_count()
     ms_dev, w = timed(step_dev, args.steps); windows.append(w)
     launches = eng.launch_count() - l0
-    ms_e2e, w = timed(step_host, args.steps); windows.append(w)
+    ms_e2e, w = timed(run_host, args.steps, whole=True); windows.append(w)
     # per-kernel-family device time: same step, same inputs, CUDA-event brackets on the launch stream
     eng.profile(True)
     _, w = timed(step_dev, args.steps); windows.append(w)
@@ -302,15 +307,16 @@ def run_product(args, cfg_name, cfg):
     value = B * world * args.steps / (ms_dev * 1e-3)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = B * sh.T * sh.F * 4 + B * 4
-    d2h = 16 + B * 4 * 2 + B * sh.L * 4
+    d2h = eng.result_block_bytes          # scalars | pred | logit | w_hop0 in one copy (256-byte aligned parts)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": make_config(cfg_name, cfg, B, world, args.keep_prob),
+            "config": make_config(cfg_name, cfg, B, world, args.keep_prob,
+                                  ("Zipf(%g)" % args.zipf if args.zipf else "uniform on [1,V)") + (", column 0 = one uid per sample" if args.uid_col else "")),
             "exchange": {"mode": exch.mode, "why": exch.why},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "path": "hpmn_step_host (C ABI): pinned host ids/labels -> H2D (double-buffered via hpmn_prefetch_host) -> fwd+bwd -> D2H scalars,pred,logit,weights -> sync"},
+                    "path": "hpmn_step_host_begin/_end (C ABI), two steps in flight: pinned host ids/labels -> H2D (double-buffered via hpmn_prefetch_host) -> fwd+bwd -> D2H scalars,pred,logit,weights -> host waits for each step's results"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": fams,
             "check": {"logloss": float(scal[0]), "covreg": float(scal[1])}}
@@ -329,6 +335,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the cpu_baseline sample (default: the whole batch)")
     ap.add_argument("--ref-rows", type=int, default=0, help="rows per step of the reference arm (default: the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zipf", type=float, default=0.0, help="ids ~ Zipf(a) instead of uniform (popularity skew; SURVEY.md 8d: 1.05)")
+    ap.add_argument("--uid-col", action="store_true", help="column 0 constant per sample like the real XLong feed (uid, item)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]

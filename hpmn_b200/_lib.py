@@ -75,6 +75,7 @@ SYMBOLS = {
     "hpmn_step_host": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _I, _OUT, _P, _P]),
     "hpmn_step_host_begin": (_I, [_P, _SH, _HY, _P, _P, _P, _P, _P, _P, _I, _I, _OUT, _P, _P]),
     "hpmn_step_host_end": (_I, [_P, _SH, _OUT, _P]),
+    "hpmn_output_block": (_I, [_SH, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hpmn_prefetch_host": (_I, [_P, _SH, _P, _P, _P]),
     "hpmn_clip_adam": (_I, [_P, _P, _P, _P, _P, _L, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "hpmn_debug_wgrad": (_I, [_P, _SH, _I, _P, _L, _P, _P, _P, _I, _P]),

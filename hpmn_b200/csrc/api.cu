@@ -38,6 +38,8 @@ struct hpmn_ctx {
   // feed double buffering (hpmn_prefetch_host): copy stream, completion event, what is staged where
   cudaStream_t copy;
   cudaEvent_t ev_copy, ev_consumed[2];
+  // results of a *_host step: event behind its D2H copies, keyed by the host scalars pointer (two steps may be in flight)
+  cudaEvent_t ev_out[2]; const void* out_key[2]; int out_next;
   const void* staged_ids; const void* staged_labels; int staged_slot, staged_B, cur_slot; bool consumed_valid[2];
   // row groups: the batch is cut into `groups` independent row ranges, each running its whole fwd+bwd chain on its own
   // stream, so one group's dense kernels fill the SMs while another group sits in its latency-bound recurrence
@@ -114,7 +116,7 @@ static const char* kFamilyNames[HPMN_K_COUNT] = {"gather_fwd", "inproj_gemm", "r
 
 // ---- shared plumbing ------------------------------------------------------------------------
 // Workspace = header (whole-batch staging and per-row outputs) + G group regions (activations of one row group).
-struct Hdr { size_t ids, labels, ids2, labels2, pred, logit, w_hop0, memory, scalars, total; };   // ids2/labels2: prefetch slot
+struct Hdr { size_t ids, labels, ids2, labels2, pred, logit, w_hop0, memory, scalars, out_end, total; };   // ids2/labels2: prefetch slot
 static Hdr make_hdr(const Dims& d) {
   Hdr h; size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
@@ -122,11 +124,13 @@ static Hdr make_hdr(const Dims& d) {
   h.labels = take((size_t)d.B * sizeof(int32_t));
   h.ids2 = take((size_t)d.B * d.T * d.F * sizeof(int32_t));
   h.labels2 = take((size_t)d.B * sizeof(int32_t));
+  // scalars | pred | logit | w_hop0 form one block: a host caller whose result buffers mirror it gets ONE D2H copy per step
+  h.scalars = take(4 * sizeof(float));
   h.pred = take((size_t)d.B * sizeof(float));
   h.logit = take((size_t)d.B * sizeof(float));
   h.w_hop0 = take((size_t)d.B * d.L * sizeof(float));
+  h.out_end = off;
   h.memory = take((size_t)d.B * d.L * d.H * sizeof(float));
-  h.scalars = take(4 * sizeof(float));
   h.total = off;
   return h;
 }
@@ -436,6 +440,8 @@ int hpmn_create(hpmn_ctx** out, int device) {
   cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   for (auto& ev : ctx->ev_consumed) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (auto& ev : ctx->ev_out) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  ctx->out_key[0] = ctx->out_key[1] = nullptr; ctx->out_next = 0;
   ctx->staged_ids = nullptr; ctx->staged_labels = nullptr; ctx->staged_slot = 0; ctx->staged_B = 0; ctx->cur_slot = 0;
   ctx->consumed_valid[0] = ctx->consumed_valid[1] = false;
   { const char* e_ov = getenv("HPMN_NO_OVERLAP"); ctx->overlap = !(e_ov && e_ov[0] == '1'); }
@@ -456,6 +462,7 @@ void hpmn_destroy(hpmn_ctx* ctx) {
   cudaEventDestroy(ctx->ev_zero);
   cudaEventDestroy(ctx->ev_dtable);
   cudaEventDestroy(ctx->ev_copy); for (auto& ev : ctx->ev_consumed) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_out) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->copy);
   cudaStreamDestroy(ctx->side);
   for (auto& gs : ctx->gstream) cudaStreamDestroy(gs);
@@ -882,15 +889,34 @@ int hpmn_step_host_begin(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* h
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev_consumed[slot], st));       // the slot may be refilled once everything above has read it
   ctx->consumed_valid[slot] = true;
-  CK(cudaMemcpyAsync(oh->scalars, scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  rc = copy_outputs(ctx, p, oh, cudaMemcpyDeviceToHost, st);
-  if (rc) return rc;
+  {
+    const char* hb = reinterpret_cast<const char*>(oh->scalars);
+    const bool mirrored = oh->pred && oh->logit && oh->w_hop0 && !oh->memory &&
+                          reinterpret_cast<const char*>(oh->pred) - hb == (ptrdiff_t)(p.hdr.pred - p.hdr.scalars) &&
+                          reinterpret_cast<const char*>(oh->logit) - hb == (ptrdiff_t)(p.hdr.logit - p.hdr.scalars) &&
+                          reinterpret_cast<const char*>(oh->w_hop0) - hb == (ptrdiff_t)(p.hdr.w_hop0 - p.hdr.scalars);
+    if (mirrored) {          // the host result buffers mirror the staging block (hpmn_output_block): one copy instead of four
+      CK(cudaMemcpyAsync(oh->scalars, scalars, p.hdr.out_end - p.hdr.scalars, cudaMemcpyDeviceToHost, st));
+    } else {
+      CK(cudaMemcpyAsync(oh->scalars, scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      rc = copy_outputs(ctx, p, oh, cudaMemcpyDeviceToHost, st);
+      if (rc) return rc;
+    }
+  }
+  { // hpmn_step_host_end(oh) waits for exactly this point, so that the NEXT step may already be queued behind it
+    const int k = ctx->out_next; ctx->out_next ^= 1;
+    CK(cudaEventRecord(ctx->ev_out[k], st));
+    ctx->out_key[k] = oh->scalars;
+  }
   return check_launch(ctx, "hpmn_step_host");
 }
 
 int hpmn_step_host_end(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_outputs* oh, void* stream) {
   if (!ctx || !s || !oh || !oh->scalars) return HPMN_EINVAL;
-  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  int k = -1;
+  for (int i = 0; i < 2; ++i) if (ctx->out_key[i] == oh->scalars) k = i;
+  if (k >= 0) { CK(cudaEventSynchronize(ctx->ev_out[k])); ctx->out_key[k] = nullptr; }
+  else CK(cudaStreamSynchronize((cudaStream_t)stream));
   if (oh->scalars[HPMN_S_IDERR] != 0.f)   // TF's GatherV2 raises InvalidArgumentError on CPU
     return fail(ctx, HPMN_EINVAL, "an id is outside [0, feature_size=%lld)", (long long)s->V);
   return HPMN_OK;
@@ -1005,6 +1031,15 @@ int hpmn_head_wide_bwd(hpmn_ctx* ctx, int B, int R, const hpmn_hyper* hy, const 
   launch_head_bwd(L, d, head_only_layout(R), *hy, 0, repre, labels, hparams, w.pred, drepre, hgrads, w.w, batch, (cudaStream_t)stream);
   launch_atb_batch(L, batch, (cudaStream_t)stream);
   return check_launch(ctx, "hpmn_head_wide_bwd");
+}
+
+int hpmn_output_block(const hpmn_shape* s, size_t* offsets, size_t* total) {
+  Dims d = make_dims(s);
+  if (!d.ok || !offsets || !total) return HPMN_EINVAL;
+  const Hdr h = make_hdr(d);
+  offsets[0] = 0; offsets[1] = h.pred - h.scalars; offsets[2] = h.logit - h.scalars; offsets[3] = h.w_hop0 - h.scalars;
+  *total = h.out_end - h.scalars;
+  return HPMN_OK;
 }
 
 int hpmn_nvls_allreduce(hpmn_ctx* ctx, float* multicast_ptr, int64_t n_floats, int rank, int world, int ctas, void* stream) {

@@ -143,16 +143,18 @@ class DataLoader_Mul:
 
 # ---- synthetic data of the BASELINE.json shapes -------------------------------------------------
 
-def synthetic_ids(B: int, T: int, F: int, V: int, seed: int = 1234, ragged: bool = False, zipf: float = 0.0) -> np.ndarray:
-    """ids uniform on [1,V) (worst case for caches) or Zipf(zipf); for F >= 3 column 0 is constant along t
-    (the uid column, preprocess_amazon.py:162); ragged: random-length suffix kept, prefix id 0."""
+def synthetic_ids(B: int, T: int, F: int, V: int, seed: int = 1234, ragged: bool = False, zipf: float = 0.0,
+                  uid_col: bool = False) -> np.ndarray:
+    """ids uniform on [1,V) (worst case for caches) or Zipf(zipf); for F >= 3 -- or uid_col=True, the XLong feed, whose
+    every step is (uid + offset, item) with ONE uid per sample (data_loader.py:58-67) -- column 0 is constant along t
+    (T colliding atomics per sample in the scatter-add); ragged: random-length suffix kept, prefix id 0."""
     rng = np.random.default_rng(seed)
     if zipf > 0:
         ids = (rng.zipf(zipf, size=(B, T, F)) % (V - 1) + 1).astype(np.int64)
     else:
         ids = rng.integers(1, V, size=(B, T, F), dtype=np.int64)
-    if F >= 3:
-        ids[:, :, 0] = ids[:, :1, 0]
+    if F >= 3 or uid_col:
+        ids[:, :, 0] = rng.integers(1, V, size=(B, 1), dtype=np.int64) if zipf > 0 else ids[:, :1, 0]
     if ragged:
         lens = rng.integers(min(5, T), T + 1, size=B)
         for b in range(B):

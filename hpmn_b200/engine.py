@@ -91,12 +91,19 @@ class HpmnEngine:
         # pinned host mirrors for the host-buffer entry point (feed_dict / fetches of hpmn.py:474-482)
         self.h_ids = torch.empty(B, shape.T, shape.F, dtype=torch.int32).pin_memory()
         self.h_labels = torch.empty(B, dtype=torch.int32).pin_memory()
-        self.h_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
-        self.h_pred = torch.zeros(B, dtype=torch.float32).pin_memory()
-        self.h_logit = torch.zeros(B, dtype=torch.float32).pin_memory()
-        self.h_w_hop0 = torch.zeros(B, L, dtype=torch.float32).pin_memory()
-        self._out_host = _lib.hpmn_outputs(_ptr(self.h_scalars), _ptr(self.h_pred), _ptr(self.h_logit),
-                                           _ptr(self.h_w_hop0), C.c_void_p(0))
+        # host result buffers mirror the library's device staging block (hpmn_output_block): one D2H copy per step; two sets,
+        # because step_host_stream keeps two steps in flight
+        offs, tot = (C.c_size_t * 4)(), C.c_size_t()
+        _lib.check(self.lib.hpmn_output_block(C.byref(self.cshape), offs, C.byref(tot)), self.ctx)
+
+        def result_block():
+            blk = torch.zeros(int(tot.value), dtype=torch.uint8).pin_memory()
+            f = lambda o, n: blk[int(o): int(o) + 4 * n].view(torch.float32)      # noqa: E731
+            sc, pr, lg, w0 = f(offs[0], 4), f(offs[1], B), f(offs[2], B), f(offs[3], B * L).view(B, L)
+            return blk, sc, pr, lg, w0, _lib.hpmn_outputs(_ptr(sc), _ptr(pr), _ptr(lg), _ptr(w0), C.c_void_p(0))
+        self.result_block_bytes = int(tot.value)
+        self._hblk, self.h_scalars, self.h_pred, self.h_logit, self.h_w_hop0, self._out_host = result_block()
+        self._hblk2, self.h_scalars2, self.h_pred2, self.h_logit2, self.h_w_hop02, self._out_host2 = result_block()
         self.init_parameters(seed)
         if params is not None:
             self.load_named(params)
@@ -217,6 +224,46 @@ class HpmnEngine:
             self.prefetch_host(prefetch_next[0], prefetch_next[1], B)
         _lib.check(self.lib.hpmn_step_host_end(self.ctx, C.byref(cs), C.byref(self._out_host), st), self.ctx)
         return self.h_scalars.numpy(), self.h_pred.numpy()[:B]
+
+    def step_host_stream(self, feeds, with_backward: bool = True, keep_prob: float = 1.0, seed0: int = 0, loss_batch: int = 0,
+                         after_step=None):
+        """Host buffers in, host results out for a SEQUENCE of batches, software-pipelined: `feeds` yields (pinned ids, pinned
+        labels); step i+1 is enqueued (its H2D copy double-buffered on the copy stream) before the host waits for the results of
+        step i, so the host's launch time never sits between two steps.  Yields (scalars, pred) numpy views of step i -- valid until
+        the step after next is enqueued.  after_step(i), if given, is called right after step i is enqueued (gradient exchange,
+        optimizer).  Every step still pays its own H2D and D2H inside whatever region the caller times."""
+        outs = ((self._out_host, self.h_scalars, self.h_pred), (self._out_host2, self.h_scalars2, self.h_pred2))
+        st = self._stream()
+        pending = None
+        it = iter(feeds)
+        nxt = next(it, None)
+        if nxt is not None:
+            self.prefetch_host(nxt[0], nxt[1], int(nxt[1].shape[0]))
+        i = 0
+        while nxt is not None:
+            cur, nxt = nxt, next(it, None)
+            B = int(cur[1].shape[0])
+            out, hs, hp = outs[i & 1]
+            cs = self._cshape(B)
+            hy = self._hyper(keep_prob, seed0 + i, loss_batch)
+            self.last_ids = (None, B)
+            _lib.check(self.lib.hpmn_step_host_begin(self.ctx, C.byref(cs), C.byref(hy), _ptr(cur[0]), _ptr(cur[1]), _ptr(self.params),
+                                                     _ptr(self.table), _ptr(self.grads), _ptr(self.dtable), 1, int(with_backward),
+                                                     C.byref(out), _ptr(self.workspace), st), self.ctx)
+            if after_step is not None:
+                after_step(i)
+            if nxt is not None:
+                self.prefetch_host(nxt[0], nxt[1], int(nxt[1].shape[0]))
+            if pending is not None:
+                pcs, pout, phs, php, pB = pending
+                _lib.check(self.lib.hpmn_step_host_end(self.ctx, C.byref(pcs), C.byref(pout), st), self.ctx)
+                yield phs.numpy(), php.numpy()[:pB]
+            pending = (cs, out, hs, hp, B)
+            i += 1
+        if pending is not None:
+            pcs, pout, phs, php, pB = pending
+            _lib.check(self.lib.hpmn_step_host_end(self.ctx, C.byref(pcs), C.byref(pout), st), self.ctx)
+            yield phs.numpy(), php.numpy()[:pB]
 
     def prefetch_host(self, h_ids: torch.Tensor, h_labels: torch.Tensor, B: Optional[int] = None):
         """Start the H2D copy of the NEXT batch (pinned int32 tensors) on the library's copy stream; the following

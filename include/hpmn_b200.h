@@ -176,12 +176,19 @@ int hpmn_step_host(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_
                    void* workspace, void* stream);
 
 /* The same call split in two so that other work can be queued between enqueue and wait: _begin enqueues H2D + compute +
- * D2H and returns immediately, _end synchronises the stream and reports an out-of-range id. */
+ * D2H and returns immediately, _end waits until the results of THAT step (identified by out_host->scalars) have landed in host
+ * memory and reports an out-of-range id.  Up to two steps may be in flight when they use distinct out_host buffers: _begin of
+ * step i+1 may be called before _end of step i, so the host's enqueue time of step i+1 hides behind the device time of step i. */
 int hpmn_step_host_begin(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids_host,
                          const int32_t* labels_host, const float* params, const float* table, float* grads,
                          float* dtable, int zero_dtable, int with_backward, const hpmn_outputs* out_host,
                          void* workspace, void* stream);
 int hpmn_step_host_end(hpmn_ctx*, const hpmn_shape*, const hpmn_outputs* out_host, void* stream);
+
+/* Optional single result copy: byte offsets (scalars, pred, logit, w_hop0) and total size of the block in which the library stages
+ * the fetched results on the device.  When the out_host pointers of a *_host call are laid out the same way inside one pinned
+ * block (and out_host->memory is NULL) the results come back in ONE D2H copy instead of four. */
+int hpmn_output_block(const hpmn_shape*, size_t* offsets /* [4] */, size_t* total);
 
 /* Optional double buffering of the feed: start the H2D copy of the NEXT batch (pinned host memory) on the library's copy
  * stream while the current step computes.  A following hpmn_step_host() called with the same ids_host / labels_host pointers

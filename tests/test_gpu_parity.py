@@ -600,3 +600,27 @@ def test_multi_gpu_gradient_exchange_modes_under_torchrun():
                         "127.0.0.1", "--master-port", "29533", "-m", "tools.dp_check"], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mode rows" in r.stdout and "mode nvls" in r.stdout
+
+
+def test_pipelined_host_steps_give_identical_results():
+    """HpmnEngine.step_host_stream keeps two steps in flight (hpmn_step_host_begin of step i+1 before hpmn_step_host_end of
+    step i): every step's host results must equal the one-step-at-a-time path."""
+    import torch
+    sh = HpmnShape(B=12, T=16, F=2, E=16, H=32, periods=[2, 2], L=3, hops=2, V=90)
+    osh = oracle_shape(sh)
+    params, table = O.init_params(osh, mode="stress")
+    batches = []
+    for k in range(5):
+        ids, labels = O.synthetic_batch(osh, seed=200 + k)
+        batches.append((torch.from_numpy(ids).pin_memory(), torch.from_numpy(labels).pin_memory()))
+    eng = _engine(sh, params, table, 1e-3)
+    ref = []
+    for k, (ids, labels) in enumerate(batches):
+        sc, pred = eng.step_host_pinned(True, 0.5, 7 + k, 0, True, sh.B, ids, labels)
+        ref.append((sc.copy(), pred.copy()))
+    got = [(sc.copy(), pred.copy()) for sc, pred in eng.step_host_stream(iter(batches), True, 0.5, seed0=7)]
+    assert len(got) == len(ref)
+    for (s0, p0), (s1, p1) in zip(ref, got):
+        assert np.array_equal(p0, p1)
+        np.testing.assert_allclose(s1[:3], s0[:3], rtol=1e-6)
+    eng.close()
