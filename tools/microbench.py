@@ -23,7 +23,7 @@ except Exception:
 
 CONFIGS = [(256, T, 32) for T in (64, 256, 1024, 4096)] + [(B, 1024, 32) for B in (512, 1024, 4096, 16384)] + [(256, 1024, 16), (4096, 1024, 16)]
 if len(sys.argv) > 1 and sys.argv[1] == "big":
-    CONFIGS = [(B, 1024, 32) for B in (512, 1024, 4096)]
+    CONFIGS = [(B, 1024, 32) for B in (1024, 4096, 16384)] + [(16384, 256, 32)]
 V = 4000000
 out = []
 for (B, T, H) in CONFIGS:
