@@ -733,9 +733,8 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
                     float* scalars, cudaStream_t st) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
-  if (d.H > HP)
-    return fail(ctx, HPMN_EINVAL, "hidden_size %d > 32: this build covers it in hpmn_memory_fwd / hpmn_memory_bwd (tensor-core recurrence) "
-                                  "only; the attention / head kernels are written for H <= 32", d.H);
+  if (d.H > HP && !tcrec_supported(d))
+    return fail(ctx, HPMN_EINVAL, "hidden_size %d: this build covers H <= 32 and H = 64 (F*E <= 64)", d.H);
   if (hy.loss_batch <= 0) hy.loss_batch = d.B;          // the groups must divide the log-loss by the whole batch
   // Wavefront kernels: 2 samples per CTA (1 for L > 5), one CTA per SM (shared memory).  They minimise the latency of
   // one wave; with more samples than one wave holds, the per-layer kernels (one warp per sample, ~12 resident per SM)

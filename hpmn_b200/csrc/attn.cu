@@ -31,12 +31,14 @@ constexpr int NT = 256;               // threads per CTA
 // backward: float4 loads along a row, lanes over the row.
 constexpr int A1S = ATT1 + 4;
 constexpr int A2S = ATT2 + 4;
-constexpr int PF1 = (4 * HP * ATT1 / 4 + NT - 1) / NT;   // float4s of A1 per thread (10)
 constexpr int PF2 = (ATT1 * ATT2 / 4 + NT - 1) / NT;     // float4s of A2 per thread (4)
+// HPT: hidden width the kernels are compiled for -- 32 (one warp; every reference configuration) or 64 (tensor-core recurrence)
 
 // One hop's score-MLP weights on their way from L2 to shared memory.  fetch() only issues the loads, so the hop that
 // is being computed hides their latency; put() lands them once every reader of the previous weights has passed a barrier.
+template <int HPT>
 struct WPref {
+  static constexpr int PF1 = (4 * HPT * ATT1 / 4 + NT - 1) / NT;   // float4s of A1 per thread (10 at 32, 20 at 64)
   float4 a1[PF1], a2[PF2];
   float a3, b1, b2;
   __device__ __forceinline__ void fetch(const float* __restrict__ P, const AttnArgs& a, int hop, int H4) {
@@ -71,7 +73,8 @@ struct WPref {
 };
 
 // covariance pieces shared by fwd and bwd: centred memory mean per slot, off-diagonal C, Frobenius norm
-__device__ __forceinline__ float covreg_block(const float (*sM)[HP], float* sMean, float (*sC)[ML], float* sRed, int L,
+template <int HPT>
+__device__ __forceinline__ float covreg_block(const float (*sM)[HPT], float* sMean, float (*sC)[ML], float* sRed, int L,
                                               int H) {
   const int tid = threadIdx.x;
   if (tid < L) {
@@ -100,26 +103,28 @@ __device__ __forceinline__ float covreg_block(const float (*sM)[HP], float* sMea
 }
 
 // dynamic shared memory carve-up (floats; every block starts on a 16-byte boundary)
+template <int HPT>
 struct AttSmem {
   float *A1, *A2, *A3, *B1, *B2, *Inp, *Z1, *Z2;
   __device__ AttSmem(float* base, int H4) {
     A1 = base; A2 = A1 + H4 * A1S; A3 = A2 + ATT1 * A2S; B1 = A3 + ATT2; B2 = B1 + ATT1;
-    Inp = B2 + ATT2; Z1 = Inp + ML * 4 * HP; Z2 = Z1 + ML * ATT1;
+    Inp = B2 + ATT2; Z1 = Inp + ML * 4 * HPT; Z2 = Z1 + ML * ATT1;
   }
-  static size_t bytes(int H4) { return sizeof(float) * (size_t)(H4 * A1S + ATT1 * A2S + 2 * ATT2 + ATT1 + ML * 4 * HP + ML * ATT1 + ML * ATT2); }
+  static size_t bytes(int H4) { return sizeof(float) * (size_t)(H4 * A1S + ATT1 * A2S + 2 * ATT2 + ATT1 + ML * 4 * HPT + ML * ATT1 + ML * ATT2); }
 };
 
-constexpr int QS = HP + 1;             // padded row stride of the staged Wq / Hmap (column and row access conflict free)
-
-// Wq [D,H] and Hmap [H,H] -> shared memory (coalesced; rows padded to QS)
+// Wq [D,H] and Hmap [H,H] -> shared memory (coalesced; rows padded to QS = HPT + 1: column and row access conflict free)
+template <int QS>
 __device__ __forceinline__ void stage_qmaps(const float* __restrict__ P, const AttnArgs& a, float* sWq, float* sHm) {
   const int tid = threadIdx.x, H = a.H, D = a.D;
   for (int e = tid; e < D * H; e += NT) sWq[(e / H) * QS + e % H] = __ldg(P + a.Wq + e);
   for (int e = tid; e < H * H; e += NT) sHm[(e / H) * QS + e % H] = __ldg(P + a.Hmap + e);
 }
 
-__global__ void __launch_bounds__(NT, 2)
+template <int HPT>
+__global__ void __launch_bounds__(NT, HPT == 32 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr int HP = HPT, QS = HPT + 1;
   extern __shared__ __align__(16) float dsm[];
   __shared__ __align__(16) float sM[ML][HP];
   __shared__ float sC[ML][ML];
@@ -132,17 +137,17 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
   pdl_wait();                                           // launched early (launch_pdl): the wavefront kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
-  AttSmem S(dsm, H4);
+  AttSmem<HPT> S(dsm, H4);
   const float* __restrict__ P = a.params;
-  WPref wp;
+  WPref<HPT> wp;
   wp.fetch(P, a, 0, H4);
   for (int e = tid; e < L * H; e += NT) sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e);
   for (int e = tid; e < D; e += NT) sLast[e] = __ldg(a.x + ((int64_t)b * a.Tpad + a.last_tp) * D + e);
   const float bqv = tid < H ? __ldg(P + a.bq + tid) : 0.f;
-  stage_qmaps(P, a, sWq, sHm);
+  stage_qmaps<QS>(P, a, sWq, sHm);
   wp.put(H4, S.A1, S.A2, S.A3, S.B1, S.B2);
   __syncthreads();
-  const float nrm = covreg_block(sM, sMean, sC, sRed, L, H);          // hpmn.py:161-170
+  const float nrm = covreg_block<HPT>(sM, sMean, sC, sRed, L, H);     // hpmn.py:161-170
   if (tid == 0) atomicAdd(a.scalars + HPMN_S_COVREG, nrm);
   if (tid < H) {                                                       // query = dense(last, H), hpmn.py:173
     float q0 = bqv, q1 = 0.f;
@@ -232,13 +237,13 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
         if (hop == 0) a.w_hop0[(int64_t)b * L + lane] = w;             // weights[0], hpmn.py:182
       }
       __syncwarp();
-      if (lane < H) {                                                  // query = query @ H + read, hpmn.py:179
+      for (int j = lane; j < H; j += 32) {                             // query = query @ H + read, hpmn.py:179
         float qn = 0.f, qm = 0.f;
-        for (int l = 0; l < L; ++l) qn = fmaf(sW[l], sM[l][lane], qn);   // hpmn.py:143-144
-        for (int i = 0; i < H; ++i) qm = fmaf(sQ[i], sHm[i * QS + lane], qm);
+        for (int l = 0; l < L; ++l) qn = fmaf(sW[l], sM[l][j], qn);      // hpmn.py:143-144
+        for (int i = 0; i < H; ++i) qm = fmaf(sQ[i], sHm[i * QS + j], qm);
         qn += qm;
-        sQn[lane] = qn;
-        a.ws.q[((int64_t)(hop + 1) * B + b) * H + lane] = qn;
+        sQn[j] = qn;
+        a.ws.q[((int64_t)(hop + 1) * B + b) * H + j] = qn;
       }
     }
     // every thread is past its last read of this hop's weights (barrier after fc3): land the next hop's
@@ -251,8 +256,10 @@ attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
   for (int e = tid; e < D; e += NT) a.repre[(int64_t)b * (H + D) + H + e] = sLast[e];
 }
 
-__global__ void __launch_bounds__(NT, 2)
+template <int HPT>
+__global__ void __launch_bounds__(NT, HPT == 32 ? 2 : 1)
 attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr int HP = HPT, QS = HPT + 1;
   extern __shared__ __align__(16) float dsm[];
   __shared__ __align__(16) float sM[ML][HP];
   __shared__ float sDm[ML][HP];
@@ -265,13 +272,13 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
   pdl_wait();                                           // launched early itself: the head kernel in front must be complete
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, H = a.H, D = a.D, B = a.B, H4 = 4 * H;
-  AttSmem S(dsm, H4);                       // S.Inp holds d(inp); S.Z1 / S.Z2 hold z then dz
+  AttSmem<HPT> S(dsm, H4);                  // S.Inp holds d(inp); S.Z1 / S.Z2 hold z then dz
   const float* __restrict__ P = a.params;
-  WPref wp;
+  WPref<HPT> wp;
   wp.fetch(P, a, a.hops - 1, H4);
   for (int e = tid; e < L * H; e += NT) { sM[e / H][e % H] = __ldg(a.memory + (int64_t)b * L * H + e); sDm[e / H][e % H] = 0.f; }
   for (int e = tid; e < D; e += NT) sDlast[e] = __ldg(a.drepre + (int64_t)b * (H + D) + H + e);
-  stage_qmaps(P, a, sWq, sHm);
+  stage_qmaps<QS>(P, a, sWq, sHm);
   if (tid < H) {
     const float g = __ldg(a.drepre + (int64_t)b * (H + D) + tid);
     sDq[tid] = g;
@@ -293,10 +300,13 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
       sDqin[tid] = s0;
     }
     for (int l = warp; l < L; l += NT / 32) {
-      const float dq = lane < H ? sDq[lane] : 0.f;
-      const float m = lane < H ? sM[l][lane] : 0.f;
-      if (lane < H) sDm[l][lane] = fmaf(dq, sW[l], sDm[l][lane]);
-      const float dw = warp_sum(m * dq);
+      float part = 0.f;
+      for (int j = lane; j < H; j += 32) {
+        const float dq = sDq[j], m = sM[l][j];
+        sDm[l][j] = fmaf(dq, sW[l], sDm[l][j]);
+        part = fmaf(m, dq, part);
+      }
+      const float dw = warp_sum(part);
       if (lane == 0) sDw[l] = dw;
     }
     __syncthreads();
@@ -393,7 +403,7 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     a.dlast[(int64_t)b * D + i] = s;
   }
   // covreg adjoint: d||offdiag C||_F = C_off / ||.|| ;  C = mc mc^T / H ; mc = M - mean_j
-  const float nrm = covreg_block(sM, sMean, sC, sRed, L, H);
+  const float nrm = covreg_block<HPT>(sM, sMean, sC, sRed, L, H);
   const float scale = nrm > 0.f ? a.memory_reg * 2.f / ((float)H * nrm) : 0.f;   // TF yields NaN at nrm == 0; we yield 0
   for (int e = tid; e < L * H; e += NT) {
     const int l = e / H, j = e % H;
@@ -431,9 +441,15 @@ void launch_attn_fwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
                      cudaStream_t st) {
   AttnArgs a = make_args(d, pl, last_offset, memory, x, params, ws);
   a.repre = repre; a.w_hop0 = w_hop0; a.scalars = scalars;
-  const size_t dsm = AttSmem::bytes(4 * d.H);
-  cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-  launch_pdl(attn_fwd_kernel, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  if (d.H <= 32) {
+    const size_t dsm = AttSmem<32>::bytes(4 * d.H);
+    cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    launch_pdl(attn_fwd_kernel<32>, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  } else {
+    const size_t dsm = AttSmem<64>::bytes(4 * d.H);
+    cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    launch_pdl(attn_fwd_kernel<64>, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  }
   ++*L.counter;
 }
 
@@ -442,9 +458,15 @@ void launch_attn_bwd(const Launch& L, const Dims& d, const ParamLayout& pl, int 
                      float* dlast, float* grads, const AttWs& ws, AtbBatch& batch, cudaStream_t st) {
   AttnArgs a = make_args(d, pl, last_offset, memory, x, params, ws);
   a.drepre = drepre; a.dmemory = dmemory; a.dlast = dlast; a.memory_reg = memory_reg;
-  const size_t dsm = AttSmem::bytes(4 * d.H);
-  cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-  launch_pdl(attn_bwd_kernel, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  if (d.H <= 32) {
+    const size_t dsm = AttSmem<32>::bytes(4 * d.H);
+    cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    launch_pdl(attn_bwd_kernel<32>, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  } else {
+    const size_t dsm = AttSmem<64>::bytes(4 * d.H);
+    cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    launch_pdl(attn_bwd_kernel<64>, dim3(d.B), dim3(NT), (size_t)dsm, st, a);
+  }
   ++*L.counter;
   // weight gradients: reductions over the batch, queued for one batched launch
   auto add = [&](const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int I, int N) {

@@ -48,7 +48,7 @@ typedef struct hpmn_shape {
   int32_t T;           /* id steps per sample as fed (user_maxlen, code/hpmn.py:249) */
   int32_t F;           /* id features per step (user_dim) */
   int32_t E;           /* embedding_size (multiple of 4) */
-  int32_t H;           /* hidden_size (<= 32 in this build) */
+  int32_t H;           /* hidden_size: <= 32, or 64 (tensor-core recurrence; attention kernels compiled for 64 lanes) */
   int32_t L;           /* number of GRU layers (user_num_layers) */
   int32_t hops;        /* self.hop */
   int32_t front_pad;   /* zero steps prepended: Hpmn_Industry 23 (code/hpmn.py:288-289), Hpmn 0 */

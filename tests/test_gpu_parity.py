@@ -55,6 +55,10 @@ CASES = {
     "many_rows_B67": (HpmnShape(B=67, T=16, F=2, E=16, H=32, periods=[2, 2, 2], L=4, hops=3, V=97), True),
     # 6 layers: the wavefront kernels switch to one sample per CTA; mixed periods 2,3,1,2,5
     "deep_L6_mixed_periods": (HpmnShape(B=5, T=120, F=2, E=16, H=32, periods=[2, 3, 1, 2, 5], L=6, hops=2, V=211), True),
+    # hidden 64: tensor-core recurrence + the 64-lane attention kernels (hidden_size is a free constructor argument, hpmn.py:218-239)
+    "hidden64_L3": (HpmnShape(B=37, T=24, F=2, E=16, H=64, periods=[2, 3], L=3, hops=3, V=300), True),
+    "hidden64_industry_F3": (HpmnShape(B=9, T=29, F=3, E=16, H=64, periods=[2, 2, 2], L=4, hops=2, V=300, front_pad=3,
+                                       mask_id0=False, last_offset=2), False),
     # long enough for several TMA chunks per layer and a ragged last chunk (T=75 -> 75/25/5 steps)
     "ragged_chunks_T75": (HpmnShape(B=4, T=75, F=2, E=16, H=24, periods=[3, 5], L=3, hops=3, V=131), True),
 }
