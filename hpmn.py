@@ -102,6 +102,10 @@ def main(argv=None):
         return 1
     if rank == 0:
         print("best test AUC: %.5f" % best)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     return 0
 
 

@@ -119,6 +119,21 @@ gather_bwd_kernel(const __grid_constant__ ScatterSources srcs, float* __restrict
   }
 }
 
+// resident 256-thread blocks per SM of a kernel on the CURRENT device (register-limited), queried once per device
+template <class K>
+static int resident_blocks(K kern) {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 256, 0) != cudaSuccess || n < 1) n = 4;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
 // all blocks resident at once (per_sm per SM), every thread running the same number of full U-batches
 static inline int grid_for(int64_t total, int threads, int sms, int per_sm) {
   int64_t need = (total + threads - 1) / threads;
@@ -132,9 +147,7 @@ void launch_gather_fwd(const Launch& L, const Dims& d, bool mask_id0, int front_
                        const float* table, float* x, float* iderr, cudaStream_t st) {
   int E4 = d.E / 4;
   int64_t total = (int64_t)d.B * d.Tpad * d.F * E4;
-  static int per_sm = 0;     // resident 256-thread blocks per SM (register-limited), queried once
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_fwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
-    per_sm = 4;
+  const int per_sm = resident_blocks(gather_fwd_kernel<4, uint32_t>);
   int grid = grid_for(total, 256 * 4, L.sms, per_sm);
   // rows of at most 64 bytes: ask L2 for 64-byte fills (HPMN_GATHER_L2_64=0 restores the default 128-byte granularity)
   static const int l2_64_env = [] { const char* e = getenv("HPMN_GATHER_L2_64"); return e ? atoi(e) : 1; }();
@@ -153,9 +166,7 @@ void launch_gather_bwd_multi(const Launch& L, const Dims& d, bool mask_id0, int 
                              cudaStream_t st) {
   int E4 = d.E / 4;
   int64_t total = (int64_t)d.B * d.T * d.F * E4;
-  static int per_sm = 0;
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_bwd_kernel<4, uint32_t>, 256, 0) != cudaSuccess || per_sm < 1))
-    per_sm = 4;
+  const int per_sm = resident_blocks(gather_bwd_kernel<4, uint32_t>);
   for (int s0 = 0; s0 < nsrc; s0 += 15) {
     const int n = nsrc - s0 < 15 ? nsrc - s0 : 15;
     ScatterSources S; memset(&S, 0, sizeof(S));
