@@ -926,11 +926,15 @@ template <int H, int DP>
 static bool tcr_fwd_go(const Launch& L, const Dims& d, const TcrLayout& tl, int k, char* ws, float* memory, cudaStream_t st) {
   static const bool stg_env = [] { const char* e = getenv("HPMN_TCR_STAGE"); return !(e && e[0] == '0'); }();
   constexpr bool CAN_STAGE = H == 32;
-  const bool stg = CAN_STAGE && stg_env;
-  int nxb = (stg ? 2 : 4) * (DP / 32);
-  while (nxb > 1 && tcr_fwd_smem(H, DP, nxb, stg) > 227 * 1024) --nxb;
-  if (tcr_fwd_smem(H, DP, nxb, stg) > 227 * 1024) return false;
-  if (nxb > 8) nxb = 8;
+  bool stg = CAN_STAGE && stg_env;
+  int nxb = 2 * (DP / 32);                         // staged: two steps of x K-blocks beside the four staging tiles
+  if (stg && tcr_fwd_smem(H, DP, nxb, true) > 227 * 1024) stg = false;
+  if (!stg) {
+    nxb = 4 * (DP / 32);
+    while (nxb > 1 && tcr_fwd_smem(H, DP, nxb, false) > 227 * 1024) --nxb;
+    if (tcr_fwd_smem(H, DP, nxb, false) > 227 * 1024) return false;
+    if (nxb > 8) nxb = 8;
+  }
   CUtensorMap tm_xh, tm_xl, tm_w, tm_st;
   const float* xh = reinterpret_cast<const float*>(ws + tl.xh[k]);
   const float* xl = reinterpret_cast<const float*>(ws + tl.xl[k]);

@@ -51,11 +51,16 @@ class HpmnEngine:
         self.symmetric = bool(symmetric)
         n_flat = (self.flat.numel() + 3) & ~3
         if self.symmetric:
-            import torch.distributed._symmetric_memory as symm_mem
-            self.flat_grad_sym = symm_mem.empty(n_flat, dtype=torch.float32, device=self.device)
-            self.flat_grad_sym.zero_()
-            self.flat_grad = self.flat_grad_sym[: self.flat.numel()]
-        else:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.flat_grad_sym = symm_mem.empty(n_flat, dtype=torch.float32, device=self.device)
+                self.flat_grad_sym.zero_()
+                self.flat_grad = self.flat_grad_sym[: self.flat.numel()]
+            except Exception as e:  # noqa: BLE001 -- no symmetric memory on this system: plain buffers, NCCL exchange
+                import warnings
+                warnings.warn("symmetric memory unavailable (%s): gradients will be exchanged with ncclAllReduce" % (str(e)[:120],))
+                self.symmetric = False
+        if not self.symmetric:
             self.flat_grad = torch.zeros_like(self.flat)
         self.comm_stream = None
         self.params = self.flat[: self.n_params]
@@ -76,7 +81,7 @@ class HpmnEngine:
             self.ws_sym = symm_mem.empty(((ws_bytes + 255) & ~255) + self.ids_bytes, dtype=torch.uint8, device=self.device)
             self.workspace = self.ws_sym[:ws_bytes]
             self.ids_sym = self.ws_sym[(ws_bytes + 255) & ~255:].view(torch.int32).view(shape.B, shape.T, shape.F)
-        else:
+        if not self.symmetric:
             self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             self.ids_sym = None
         self.last_ids = None          # (tensor or None, rows): ids the last backward call consumed (None: the host entry point's slot)
