@@ -425,7 +425,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   { const char* e_tc = getenv("HPMN_NO_TC"); ctx->use_tc = !(e_tc && e_tc[0] == '1'); }
   { const char* e_w = getenv("HPMN_NO_WAVE"); ctx->use_wave = !(e_w && e_w[0] == '1'); }
   { const char* e_t = getenv("HPMN_TCREC"); ctx->tcrec_mode = e_t ? atoi(e_t) : -1;
-    const char* e_b = getenv("HPMN_TCREC_MIN_B"); ctx->tcrec_min_b = e_b ? atoi(e_b) : 2048; }
+    const char* e_b = getenv("HPMN_TCREC_MIN_B"); ctx->tcrec_min_b = e_b ? atoi(e_b) : 8192; }
   memset(ctx->ms, 0, sizeof(ctx->ms)); memset(ctx->calls, 0, sizeof(ctx->calls));
   cudaSetDevice(device);
   e = cudaMalloc(&ctx->scratch, 256);

@@ -1,7 +1,8 @@
 """python -m tools.microbench : BASELINE.json configs[4] -- gather + periodic-GRU microbench.
 
-Sweeps seq_len 64..4096 and batch 256..16384 (hidden 16 / 32; H in {64,128} needs the large-H kernels that are not in this
-build) on synthetic ids, 5 layers period 2, V = 4 M, and reports per configuration: step time, samples/s, gather GB/s against
+Sweeps seq_len 64..4096, batch 256..16384 and hidden {16, 32, 64} (H = 64 and B >= 2048 run the memory on the tensor-core
+recurrence, csrc/tcrec.cu; H = 128 is not built: DESIGN.md section 1) on synthetic ids, 5 layers period 2, V = 4 M, and reports
+per configuration: step time, samples/s, gather GB/s against
 the measured HBM peak, and the GRU's algorithmic TFLOP/s (fwd+bwd = 3 x fwd) over the time of the kernels that do GRU work.
 Writes gpurun_out/microbench.json; one line per configuration on stdout."""
 import json
@@ -21,7 +22,8 @@ try:
 except Exception:
     HBM = 6650.0
 
-CONFIGS = [(256, T, 32) for T in (64, 256, 1024, 4096)] + [(B, 1024, 32) for B in (512, 1024, 4096, 16384)] + [(256, 1024, 16), (4096, 1024, 16)]
+CONFIGS = ([(256, T, H) for H in (16, 32, 64) for T in (64, 256, 1024, 4096)] + [(B, 1024, 32) for B in (1024, 4096, 16384)] +
+           [(B, 1024, 64) for B in (4096, 16384)] + [(4096, 1024, 16)])
 if len(sys.argv) > 1 and sys.argv[1] == "big":
     CONFIGS = [(B, 1024, 32) for B in (1024, 4096, 16384)] + [(16384, 256, 32)]
 V = 4000000
