@@ -17,6 +17,7 @@ using namespace hpmn;
 
 struct hpmn_ctx {
   bool wave_now;    // decided per step: the wavefront kernels are used only when the whole batch is one wave of CTAs
+  bool tc_now;      // decided per step on the WHOLE batch (row groups inherit it): memory on the tensor-core recurrence
   bool use_wave;    // fused wavefront kernels for the recurrence (HPMN_NO_WAVE=1 selects the layer-by-layer kernels)
   bool use_tc;      // tcgen05 path for the dense (non-recurrent) GEMMs; HPMN_NO_TC=1 selects the FFMA kernels
   int tcrec_mode;   // tensor-core recurrence (tcrec.cu): -1 auto (H > 32, or B >= tcrec_min_b), 0 never, 1 always (HPMN_TCREC)
@@ -669,7 +670,7 @@ static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
     launch_gather_fwd(L, d, s->mask_id0 != 0, s->front_pad, s->V, ids + (int64_t)r0 * d.T * d.F, table, x,
                       scalars + HPMN_S_IDERR, st); }
   if (ov) cudaStreamWaitEvent(st, ctx->ev_join, 0);
-  if (!(want_tcrec(ctx, d) && run_memory_fwd_tc(ctx, p, x, params, memory, st, ov)))
+  if (!(ctx->tc_now && run_memory_fwd_tc(ctx, p, x, params, memory, st, ov)))
     run_memory_fwd(ctx, p, x, params, memory, st, ov);
   { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
     launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L,
@@ -689,7 +690,7 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   const float* memory = p.hf(p.hdr.memory) + (int64_t)r0 * d.L * d.H;
   const bool ov = side_ok && ctx->overlap && !ctx->profile;
   // the tensor-core recurrence keeps its own activations (they alias the wavefront path's: one of the two runs per call)
-  const bool tc = want_tcrec(ctx, d);
+  const bool tc = ctx->tc_now;
   float* dx0 = tc ? reinterpret_cast<float*>(p.ws + p.wl.tcr + make_tcr_layout(d).dx[0]) : p.f(p.wl.dxk[0]);
   AtbBatch batch; batch.n = 0; batch.blocks = 0;
   { Bracket b(ctx, st, HPMN_K_HEAD_BWD);
@@ -740,6 +741,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   // one wave; with more samples than one wave holds, the per-layer kernels (one warp per sample, ~12 resident per SM)
   // have the higher throughput (tools/microbench.py).
   { const int nspc = d.L <= 5 ? 2 : 1; ctx->wave_now = (d.B + nspc - 1) / nspc <= ctx->sms; }
+  ctx->tc_now = want_tcrec(ctx, d);
   // co-running dense kernels steal issue slots from the latency-critical recurrent warps, so grouping only pays
   // once every group still fills the machine (measured: -4 % at B=256, +11 % at B=1024)
   int G = ctx->profile ? 1 : ctx->groups;
