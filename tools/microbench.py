@@ -25,7 +25,7 @@ except Exception:
 CONFIGS = ([(256, T, H) for H in (16, 32, 64) for T in (64, 256, 1024, 4096)] + [(B, 1024, 32) for B in (1024, 4096, 16384)] +
            [(B, 1024, 64) for B in (4096, 16384)] + [(4096, 1024, 16)])
 if len(sys.argv) > 1 and sys.argv[1] == "big":
-    CONFIGS = [(B, 1024, 32) for B in (1024, 4096, 16384)] + [(16384, 256, 32)]
+    CONFIGS = [(B, 1024, 32) for B in (1024, 4096, 16384)] + [(16384, 256, 32), (65536, 256, 32)]
 V = 4000000
 out = []
 for (B, T, H) in CONFIGS:
