@@ -72,7 +72,7 @@ class _Side:
 
 class HpmnDualEngine:
     def __init__(self, user_shape: HpmnShape, item_shape: HpmnShape, device: int = 0, memory_reg: float = 1e-5,
-                 table: Optional[np.ndarray] = None, params: Optional[Dict[str, np.ndarray]] = None, seed: int = 4321):
+                 l2_reg: float = 0.0, table: Optional[np.ndarray] = None, params: Optional[Dict[str, np.ndarray]] = None, seed: int = 4321):
         if not torch.cuda.is_available():
             raise RuntimeError("hpmn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if (user_shape.B, user_shape.E, user_shape.H, user_shape.V) != (item_shape.B, item_shape.E, item_shape.H, item_shape.V):
@@ -85,7 +85,7 @@ class HpmnDualEngine:
         ctx = C.c_void_p()
         _lib.check(self.lib.hpmn_create(C.byref(ctx), device))
         self.ctx = ctx
-        self.memory_reg = float(memory_reg)
+        self.memory_reg, self.l2_reg = float(memory_reg), float(l2_reg)
         self.user, self.item = _Side(self.lib, user_shape, self.device), _Side(self.lib, item_shape, self.device)
         self.B, self.V, self.E = user_shape.B, user_shape.V, user_shape.E
         self.R = (user_shape.H + user_shape.D) + (item_shape.H + item_shape.D)
@@ -178,6 +178,14 @@ class HpmnDualEngine:
         _lib.check(lib.hpmn_head_wide_fwd(ctx, n, self.R, C.byref(hy), _ptr(self.repre), _ptr(labels), _ptr(self.hparams),
                                           _ptr(self.pred), _ptr(self.logit), _ptr(self.scalars), _ptr(self.hws), st), ctx)
         self.scalars[2] = self.scalars[0] + self.memory_reg * self.scalars[1]      # loss = logloss + memory_reg * memory_loss
+        if self.l2_reg != 0.0:      # + l2_reg * tf.nn.l2_loss(v) over every trainable, the table included (hpmn.py:204-205)
+            for p in self._l2_buffers():
+                self.scalars[2] += 0.5 * self.l2_reg * (p[0] * p[0]).sum()
+
+    def _l2_buffers(self):
+        """(variables, gradients) the l2 term covers; the unused output/* slots of the side blocks are zeros"""
+        return [(self.user.params, self.user.grads), (self.item.params, self.item.grads), (self.hparams, self.hgrads),
+                (self.table.view(-1), self.dtable.view(-1))]
 
     def forward_backward(self, user_ids: torch.Tensor, item_ids: torch.Tensor, labels: torch.Tensor, keep_prob: float = 1.0,
                          seed: int = 0):
@@ -200,12 +208,14 @@ class HpmnDualEngine:
             _lib.check(lib.hpmn_memory_bwd(ctx, c, _ptr(side.x), _ptr(side.params), _ptr(side.dmemory), _ptr(side.dx), _ptr(side.grads),
                                            _ptr(side.ws), st), ctx)
             _lib.check(lib.hpmn_gather_bwd(ctx, c, _ptr(ids), _ptr(side.dx), _ptr(side.dlast), _ptr(self.dtable), st), ctx)
+        if self.l2_reg != 0.0:
+            for p, g in self._l2_buffers():
+                g.add_(p, alpha=self.l2_reg)
 
     def apply_gradients(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, clip: float = 1.0):
         """clip_by_value + Adam over every trainable (hpmn.py:209-214); the unused output/* slots of the side blocks have zero
         gradients and stay at their initial value."""
-        bufs = [(self.user.params, self.user.grads), (self.item.params, self.item.grads), (self.hparams, self.hgrads),
-                (self.table.view(-1), self.dtable.view(-1))]
+        bufs = self._l2_buffers()
         if self._adam is None:
             self._adam = [(torch.zeros_like(p), torch.zeros_like(p)) for p, _ in bufs]
         self.adam_t += 1

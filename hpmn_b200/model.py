@@ -89,7 +89,7 @@ class Hpmn_Basic(object):
             item_shape.steps()
             self.item_shape = item_shape
             self.engine = HpmnDualEngine(user_shape, item_shape, device=self._device, memory_reg=self.memory_reg,
-                                         table=self.emb_initializer, seed=self._seed)
+                                         l2_reg=self.l2_reg, table=self.emb_initializer, seed=self._seed)
             return
         from . import dist as hd
         world = hd.rank_world()[1]

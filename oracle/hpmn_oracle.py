@@ -5,19 +5,23 @@ This file is a NumPy restatement of the reference TF1.4 graph built by
 never the product.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import it.  The product package (hpmn_b200/) must not.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or recorded outputs for this
-path, TensorFlow 1.4 and Python 2 cannot be installed in this
-image, and the arithmetic of the path lives in that un-vendored third-party dependency
-(readme.md:17 pins it only as "Tensorflow 1.4").  The restatement therefore follows, in
-order of authority:
-  1. code/hpmn.py:113-214, 266-320, 414-465   graph wiring, shapes, constants
+PARITY: GRAPH WIRING PINNED, TF OP ARITHMETIC UNPINNED.  The reference ships no tests, golden vectors or recorded
+outputs for this path, TensorFlow 1.4 and Python 2 cannot be installed in this image, and the
+arithmetic of the ops lives in that un-vendored third-party dependency (readme.md:17 pins it only as "Tensorflow 1.4").
+What is pinned: tests/golden/refgraph_*.npz are produced by importing the reference's code/hpmn.py UNMODIFIED on a TF1-API
+stand-in (tests/golden/tf1_shim.py, generator tests/golden/make_reference_graph_fixture.py) and recording what its own
+graph computes; tests/test_reference_graph.py checks this file against them (outputs 1e-13, gradients 1e-8, two
+clip + Adam steps).  What is not: the arithmetic inside GRUCell / dense / batch_normalization / log_loss / Adam, which the
+stand-in restates from TF1.4's published behaviour just like this file does -- no real TF1.4 session ever ran.
+The restatement follows, in order of authority:
+  1. code/hpmn.py:113-214, 266-320, 414-465   graph wiring, shapes, constants          (pinned, see above)
   2. code/util.py:81-110 (minus line 108)     in-tree copy of the TF1.4 GRUCell arithmetic
   3. code/rnn.py:588, 627-807                 dynamic_rnn loop semantics (zero state, no length mask)
   4. code/util.py:152-159                     front padding of the input tuples
   5. published TF1.4 defaults (glorot-uniform kernels, gate bias 1, BN eps 1e-3 momentum .99
      training=False, log_loss eps 1e-7 mean reduction, dropout scales by 1/keep_prob)
 Each function cites the reference lines it restates.  Self-made golden vectors (fp64 run of this
-file, tests/golden/) pin the CUDA path to THIS restatement, not to TensorFlow.
+file, tests/golden/{amazon,taobao,xlong}_*.npz) pin the CUDA path to THIS restatement.
 
 Everything is written batch-vectorised with an explicit Python loop over time steps, in a
 caller-chosen dtype (np.float64 for the checker, np.float32 to measure fp32 round-off).

@@ -1,7 +1,8 @@
 """Generate the golden fixtures under tests/golden/ from the fp64 oracle (python -m oracle.make_golden).
 
-PARITY UNPINNED: these vectors pin the CUDA path (and future edits of the oracle) to THIS restatement
-of the reference graph, not to TensorFlow 1.4 -- the reference ships no outputs to compare with.
+These vectors pin the CUDA path (and future edits of the oracle) to THIS restatement
+of the reference graph, not to TensorFlow 1.4 -- the reference ships no outputs to compare with (the fixtures made from the
+reference's own graph code are tests/golden/refgraph_*.npz, see tests/golden/make_reference_graph_fixture.py).
 Inputs are regenerated from the seeds stored in each file; only outputs / gradients are stored."""
 from __future__ import annotations
 

@@ -1,6 +1,7 @@
 """TF1-equivalent restatement of the HPMN graph in torch-CPU  --  TEST / BASELINE INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED (see oracle/hpmn_oracle.py header): TensorFlow 1.4 cannot be installed here, so
+PARITY: graph wiring pinned to the reference's own code/hpmn.py (tests/golden/refgraph_*.npz, tests/test_reference_graph.py),
+TF1.4 op arithmetic unpinned (see oracle/hpmn_oracle.py header): TensorFlow 1.4 cannot be installed here, so
 this is a restatement, NOT TensorFlow.  It exists for two reasons:
   * an independent check of the hand-derived adjoint in hpmn_oracle.backward (torch autograd);
   * the CPU baseline ("cpu_baseline" / `bench.py --impl reference`): the graph is executed the way

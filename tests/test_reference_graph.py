@@ -1,0 +1,120 @@
+"""The oracle against the reference's OWN graph code.
+
+tests/golden/refgraph_*.npz hold what /root/reference/code/hpmn.py -- imported unmodified, its `tensorflow` resolved to
+the TF1-API stand-in tests/golden/tf1_shim.py -- computes for three configurations: variables by TF name, feeds,
+prediction / log_loss / memory_loss / cross_entropy / attention weights, compute_gradients() of every trainable, and
+the variables after two train_step runs.  These tests pin the oracle's restatement of the graph WIRING (hpmn.py:113-214,
+266-320, 414-465) to that; the arithmetic inside the TF ops is restated on both sides (see the shim's header)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hpmn_oracle as O
+from oracle import tf1_restatement as R
+from tests import _refgraph as G
+
+
+@pytest.mark.parametrize("name", ["refgraph_amazon", "refgraph_xlong"])
+def test_oracle_reproduces_the_reference_graph_single_side(name):
+    z, c = G.load(name)
+    sh = O.OracleShape(**G.side_kwargs(c)[0])
+    assert list(O.param_names(sh)) == [k for k in map(str, z["trainable"]) if k != G.TABLE and k not in set(map(str, z["unused"]))]
+    p = G.trainables(z)
+    for k, shp in O.param_names(sh).items():
+        assert p[k].shape == tuple(shp), k
+    tb = z["var:" + G.TABLE].astype(np.float64)
+    f = O.forward(sh, p, tb, z["user_inp0"], z["label0"], memory_reg=c["memory_reg"], dtype=np.float64)
+    np.testing.assert_allclose(f["pred"], z["prediction"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(f["w_hop0"], z["user_weights"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose([f["logloss"], f["covreg"], f["loss"]], [z["log_loss"], z["memory_loss"], z["cross_entropy"]],
+                               rtol=1e-12, atol=1e-15)
+    g, dt = O.backward(sh, f, z["user_inp0"], z["label0"], memory_reg=c["memory_reg"])
+    for k in p:
+        np.testing.assert_allclose(g[k], z["grad:" + k], rtol=1e-8, atol=1e-13, err_msg=k)
+    np.testing.assert_allclose(dt, G.dense_rows(z, "grad", sh.V, sh.E), rtol=1e-8, atol=1e-13)
+
+    # the two train_step runs: clip_by_value(-1, 1) + Adam on every trainable, the table densely (hpmn.py:209-214)
+    var = dict(p); var[G.TABLE] = tb
+    slots = {k: (np.zeros_like(v), np.zeros_like(v)) for k, v in var.items()}
+    for t in (1, 2):
+        if t == 2:
+            f = O.forward(sh, {k: v for k, v in var.items() if k != G.TABLE}, var[G.TABLE], z["user_inp1"], z["label1"],
+                          memory_reg=c["memory_reg"], dtype=np.float64)
+            g, dt = O.backward(sh, f, z["user_inp1"], z["label1"], memory_reg=c["memory_reg"])
+        g = dict(g); g[G.TABLE] = dt
+        for k in var:
+            O.clip_adam_step(var[k], g[k], slots[k][0], slots[k][1], t, lr=c["lr"])
+    for k in p:        # `after:` is stored in float32: 6e-8 relative, the two updates are ~1e-3 each
+        np.testing.assert_allclose(var[k], z["after:" + k], rtol=1e-7, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(var[G.TABLE], G.dense_rows(z, "after", sh.V, sh.E, base=tb), rtol=1e-7, atol=1e-9)
+    f = O.forward(sh, {k: v for k, v in var.items() if k != G.TABLE}, var[G.TABLE], z["user_inp0"], z["label0"],
+                  memory_reg=c["memory_reg"], dtype=np.float64)
+    np.testing.assert_allclose(f["pred"], z["prediction_after"], rtol=0, atol=1e-12)
+
+
+def test_oracle_reproduces_the_reference_graph_both_sides_with_l2():
+    """user=True, item=True, l2_reg != 0: concat of the two representations, memory_loss = imloss + umloss, l2 over
+    every trainable including the table (hpmn.py:204-205, 452-456)"""
+    import torch
+    z, c = G.load("refgraph_dual")
+    ku, ki = G.side_kwargs(c)
+    us, it = O.OracleShape(**ku), O.OracleShape(**ki)
+    p = {k: torch.tensor(v, requires_grad=True) for k, v in G.trainables(z).items()}
+    tb = torch.tensor(z["var:" + G.TABLE].astype(np.float64), requires_grad=True)
+    slots = {}
+    lab = [torch.tensor(z["label%d" % i], dtype=torch.float64) for i in (0, 1)]
+    uid = [torch.tensor(z["user_inp%d" % i], dtype=torch.int64) for i in (0, 1)]
+    iid = [torch.tensor(z["item_inp%d" % i], dtype=torch.int64) for i in (0, 1)]
+
+    def run(i):
+        out = R.forward_torch_dual(us, it, p, tb, uid[i], iid[i], lab[i], memory_reg=c["memory_reg"])
+        l2 = sum((v * v).sum() for v in p.values()) + (tb * tb).sum()
+        out["cross_entropy"] = out["loss"] + c["l2_reg"] * 0.5 * l2
+        return out
+
+    out = run(0)
+    np.testing.assert_allclose(out["pred"].detach().numpy(), z["prediction"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["user"]["w_hop0"].detach().numpy(), z["user_weights"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["item"]["w_hop0"].detach().numpy(), z["item_weights"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose([out[k].item() for k in ("logloss", "covreg", "cross_entropy")],
+                               [z["log_loss"], z["memory_loss"], z["cross_entropy"]], rtol=1e-12)
+    for t in (1, 2):
+        if t == 2:
+            out = run(1)
+        every = dict(p); every[G.TABLE] = tb
+        grads = torch.autograd.grad(out["cross_entropy"], list(every.values()))
+        for (k, v), g in zip(every.items(), grads):
+            g = g.numpy()
+            if t == 1 and k == G.TABLE:
+                np.testing.assert_allclose(g, G.dense_rows(z, "grad", us.V, us.E), rtol=1e-8, atol=1e-13)
+            elif t == 1:
+                np.testing.assert_allclose(g, z["grad:" + k], rtol=1e-8, atol=1e-13, err_msg=k)
+            m, s = slots.setdefault(k, (np.zeros_like(g), np.zeros_like(g)))
+            a = v.detach().numpy().copy()
+            O.clip_adam_step(a, g, m, s, t, lr=c["lr"])
+            with torch.no_grad():
+                v.copy_(torch.from_numpy(a))
+    for k, v in p.items():
+        np.testing.assert_allclose(v.detach().numpy(), z["after:" + k], rtol=1e-7, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(tb.detach().numpy(), G.dense_rows(z, "after", us.V, us.E, base=z["var:" + G.TABLE]),
+                               rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/code/hpmn.py"), reason="the reference is only present in the build container")
+def test_fixture_is_what_the_reference_code_computes_today():
+    """Re-runs the reference's hpmn.py on the stand-in and compares with the committed amazon fixture."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(G.GOLD)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import make_reference_graph_fixture as M; "
+            "M.HERE = sys.argv[1]; ref, tf = M.load_reference(); M.make('refgraph_amazon', ref, tf)" % G.GOLD)
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([sys.executable, "-c", code, tmp], check=True, cwd=root, stdout=subprocess.DEVNULL, timeout=300)
+        new = np.load(os.path.join(tmp, "refgraph_amazon.npz"))
+        old, _ = G.load("refgraph_amazon")
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            if old[k].dtype.kind in "fiu":
+                np.testing.assert_allclose(new[k], old[k], rtol=1e-12, atol=1e-15, err_msg=k)
