@@ -118,3 +118,25 @@ def test_fixture_is_what_the_reference_code_computes_today():
         for k in old.files:
             if old[k].dtype.kind in "fiu":
                 np.testing.assert_allclose(new[k], old[k], rtol=1e-12, atol=1e-15, err_msg=k)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/code/data_loader.py"), reason="the reference is only present in the build container")
+def test_dataloader_equals_the_reference_loader_on_the_reference_dataset_sample():
+    """code/data_loader.py runs under Python 3 as far as its plain `DataLoader` goes (DataLoader_Mul is Python-2 only:
+    `batchsize / 2` lines, list-returning map, fork-shared file handle).  Batches of the reference's own sample tuples
+    (tests/golden/amazon_hpmn_sample.pkl) through both loaders must be identical, short last batch included."""
+    import importlib.util
+    import pickle
+    spec = importlib.util.spec_from_file_location("reference_data_loader", "/root/reference/code/data_loader.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from hpmn_b200.data_loader import DataLoader
+    with open(os.path.join(G.GOLD, "amazon_hpmn_sample.pkl"), "rb") as f:
+        train = pickle.load(f)
+    train = train[:100]
+    a, b = list(ref.DataLoader(train, 48)), list(DataLoader(train, 48))
+    assert len(a) == len(b) == 3
+    for (ia, da), (ib, db) in zip(a, b):
+        assert ia == ib
+        assert list(da[0]) == list(db[0]) and list(da[2]) == list(db[2]) and list(da[4]) == list(db[4])
+        assert np.array_equal(np.asarray(da[1]), np.asarray(db[1])) and np.array_equal(np.asarray(da[3]), np.asarray(db[3]))
