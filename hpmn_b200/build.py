@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libhpmn_b200.so")
-SOURCES = ["api.cu", "embed.cu", "gemm.cu", "tc_gemm.cu", "tcrec.cu", "comm.cu", "gru.cu", "wave.cu", "attn.cu", "head.cu"]
+SOURCES = ["api.cu", "embed.cu", "gemm.cu", "tc_gemm.cu", "tcrec.cu", "comm.cu", "gru.cu", "wave.cu", "attn.cu", "head.cu", "mid.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"] + os.environ.get("HPMN_NVCC_EXTRA", "").split()

@@ -35,6 +35,8 @@ struct hpmn_ctx {
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
+  bool fuse_mid;            // training step: attention + head, forward and backward, as one kernel (mid.cu); HPMN_NO_FUSE_MID=1 disables
+  bool fuse_now;            // ... for the step being queued
   bool dtable_late;         // this step touches dtable after the scatter of the whole-batch chain (row groups, l2 term)
   // feed double buffering (hpmn_prefetch_host): copy stream, completion event, what is staged where
   cudaStream_t copy;
@@ -446,6 +448,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx->staged_ids = nullptr; ctx->staged_labels = nullptr; ctx->staged_slot = 0; ctx->staged_B = 0; ctx->cur_slot = 0;
   ctx->consumed_valid[0] = ctx->consumed_valid[1] = false;
   { const char* e_ov = getenv("HPMN_NO_OVERLAP"); ctx->overlap = !(e_ov && e_ov[0] == '1'); }
+  { const char* e_fm = getenv("HPMN_NO_FUSE_MID"); ctx->fuse_mid = !(e_fm && e_fm[0] == '1'); }
   for (auto& gs : ctx->gstream) cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking);
   for (auto& ev : ctx->ev_gdone) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_gstart, cudaEventDisableTiming);
@@ -672,6 +675,7 @@ static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   if (ov) cudaStreamWaitEvent(st, ctx->ev_join, 0);
   if (!(ctx->tc_now && run_memory_fwd_tc(ctx, p, x, params, memory, st, ov)))
     run_memory_fwd(ctx, p, x, params, memory, st, ov);
+  if (ctx->fuse_now) return;    // bwd_rows runs attention + head, both directions, as one kernel
   { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
     launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L,
                     scalars, p.att(), st); }
@@ -682,7 +686,8 @@ static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
 
 // backward chain of one row group; weight gradients accumulate into grads / dtable with atomics
 static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hpmn_hyper& hy, const int32_t* ids,
-                     const int32_t* labels, const float* params, float* grads, float* dtable, bool side_ok, cudaStream_t st) {
+                     const int32_t* labels, const float* params, float* grads, float* dtable, float* scalars, bool side_ok,
+                     cudaStream_t st) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   const int r0 = p.row0;
@@ -693,12 +698,18 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   const bool tc = ctx->tc_now;
   float* dx0 = tc ? reinterpret_cast<float*>(p.ws + p.wl.tcr + make_tcr_layout(d).dx[0]) : p.f(p.wl.dxk[0]);
   AtbBatch batch; batch.n = 0; batch.blocks = 0;
-  { Bracket b(ctx, st, HPMN_K_HEAD_BWD);
+  if (!ctx->fuse_now) {
+    Bracket b(ctx, st, HPMN_K_HEAD_BWD);
     launch_head_bwd(L, d, p.pl, hy, r0, p.f(p.wl.repre), labels + r0, params, p.hf(p.hdr.pred) + r0, p.f(p.wl.drepre), grads,
                     p.head(), batch, st); }
-  { Bracket b(ctx, st, HPMN_K_ATTN_BWD);
-    launch_attn_bwd(L, d, p.pl, s->last_offset, hy.memory_reg, memory, x, params, p.f(p.wl.drepre), p.f(p.wl.dmemory),
-                    p.f(p.wl.dlast), grads, p.att(), batch, st);
+  { Bracket b(ctx, st, ctx->fuse_now ? HPMN_K_ATTN_FWD : HPMN_K_ATTN_BWD);   // fused: the whole section is booked on ATTN_FWD
+    if (ctx->fuse_now)
+      launch_mid_fused(L, d, p.pl, hy, s->last_offset, r0, memory, x, params, labels + r0, p.f(p.wl.repre),
+                       p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L, p.hf(p.hdr.pred) + r0, p.hf(p.hdr.logit) + r0, scalars,
+                       p.f(p.wl.drepre), p.f(p.wl.dmemory), p.f(p.wl.dlast), grads, p.att(), p.head(), batch, st);
+    else
+      launch_attn_bwd(L, d, p.pl, s->last_offset, hy.memory_reg, memory, x, params, p.f(p.wl.drepre), p.f(p.wl.dmemory),
+                      p.f(p.wl.dlast), grads, p.att(), batch, st);
     if (ov) {     // joined at the end of run_memory_bwd
       cudaEventRecord(ctx->ev_fork[HPMN_MAX_LAYERS], st);
       cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS], 0);
@@ -742,6 +753,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   // have the higher throughput (tools/microbench.py).
   { const int nspc = d.L <= 5 ? 2 : 1; ctx->wave_now = (d.B + nspc - 1) / nspc <= ctx->sms; }
   ctx->tc_now = want_tcrec(ctx, d);
+  ctx->fuse_now = with_backward && ctx->fuse_mid;
   // co-running dense kernels steal issue slots from the latency-critical recurrent warps, so grouping only pays
   // once every group still fills the machine (measured: -4 % at B=256, +11 % at B=1024)
   int G = ctx->profile ? 1 : ctx->groups;
@@ -779,7 +791,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
     } }
   if (G == 1) {
     fwd_rows(ctx, p, s, hy, ids, labels, params, table, scalars, side_pack, st);
-    if (with_backward) bwd_rows(ctx, p, s, hy, ids, labels, params, grads, dtable, true, st);
+    if (with_backward) bwd_rows(ctx, p, s, hy, ids, labels, params, grads, dtable, scalars, true, st);
   } else {
     CK(cudaEventRecord(ctx->ev_gstart, st));
     const int base = d.B / G, rem = d.B % G;
@@ -790,7 +802,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
       cudaStream_t gs = ctx->gstream[g];
       CK(cudaStreamWaitEvent(gs, ctx->ev_gstart, 0));
       fwd_rows(ctx, gp, s, hy, ids, labels, params, table, scalars, false, gs);
-      if (with_backward) bwd_rows(ctx, gp, s, hy, ids, labels, params, grads, dtable, false, gs);
+      if (with_backward) bwd_rows(ctx, gp, s, hy, ids, labels, params, grads, dtable, scalars, false, gs);
       CK(cudaEventRecord(ctx->ev_gdone[g], gs));
       CK(cudaStreamWaitEvent(st, ctx->ev_gdone[g], 0));
       row0 += rows;

@@ -433,6 +433,11 @@ void launch_head_fwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_
 void launch_head_bwd(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, int row0, const float* repre,
                      const int32_t* labels, const float* params, const float* pred, float* drepre, float* grads,
                      const HeadWs& ws, AtbBatch& batch, cudaStream_t st);
+// training step: attention fwd + head fwd + head bwd + attention bwd of one sample per CTA in ONE kernel (mid.cu)
+void launch_mid_fused(const Launch&, const Dims&, const ParamLayout&, const hpmn_hyper&, int last_offset, int row0,
+                      const float* memory, const float* x, const float* params, const int32_t* labels, float* repre,
+                      float* w_hop0, float* pred, float* logit, float* scalars, float* drepre, float* dmemory, float* dlast,
+                      float* grads, const AttWs& aws, const HeadWs& hws, AtbBatch& batch, cudaStream_t st);
 
 // in-switch all-reduce of a symmetric buffer through its multicast mapping (comm.cu); ctas <= 0: one CTA per SM
 void launch_nvls_allreduce(const Launch&, float* mc, int64_t n_floats, int rank, int world, int ctas, cudaStream_t st);

@@ -94,9 +94,11 @@ def test_forward_backward_matches_oracle(name, mode):
 
 @pytest.mark.parametrize("env", [{"HPMN_NO_WAVE": "1"}, {"HPMN_NO_TC": "1"}, {"HPMN_NO_WAVE": "1", "HPMN_NO_TC": "1"},
                                  {"HPMN_GROUPS": "3", "HPMN_GROUP_MIN_ROWS": "16"}, {"HPMN_NO_OVERLAP": "1"},
-                                 {"HPMN_TCREC": "1"}, {"HPMN_TCREC": "1", "HPMN_GROUPS": "3", "HPMN_GROUP_MIN_ROWS": "16"}],
+                                 {"HPMN_TCREC": "1"}, {"HPMN_TCREC": "1", "HPMN_GROUPS": "3", "HPMN_GROUP_MIN_ROWS": "16"},
+                                 {"HPMN_NO_FUSE_MID": "1"}, {"HPMN_NO_FUSE_MID": "1", "HPMN_GROUPS": "3", "HPMN_GROUP_MIN_ROWS": "16"}],
                          ids=["layer_serial", "ffma_gemms", "layer_serial_ffma", "row_groups", "no_side_stream",
-                              "tensor_core_recurrence", "tensor_core_recurrence_row_groups"])
+                              "tensor_core_recurrence", "tensor_core_recurrence_row_groups", "separate_attention_head_kernels",
+                              "separate_attention_head_kernels_row_groups"])
 def test_alternate_kernel_paths_match_oracle(env, monkeypatch):
     """The library picks its kernels at hpmn_create() from the environment: the per-layer recurrent kernels, the fp32
     FFMA GEMMs, the concurrent row-group streams and the single-stream schedule must all give the same answer."""
