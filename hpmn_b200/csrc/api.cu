@@ -35,6 +35,7 @@ struct hpmn_ctx {
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
+  void* zero_late; size_t zero_late_bytes; void* zero_grads; size_t zero_grads_bytes;   // buffers zero_behind_projection() clears
   bool fuse_mid;            // training step: attention + head, forward and backward, as one kernel (mid.cu); HPMN_NO_FUSE_MID=1 disables
   bool fuse_now;            // ... for the step being queued
   bool dtable_late;         // this step touches dtable after the scatter of the whole-batch chain (row groups, l2 term)
@@ -306,6 +307,27 @@ static bool run_memory_bwd_tc(hpmn_ctx* ctx, const Plan& p, const float* x, cons
 }
 
 // memory forward: pack + per layer (projection GEMM, recurrence)
+// Zero the gradient buffers of this step on the side stream, starting when everything queued on `st` so far is done.  Called
+// right behind the layer-0 projection GEMM: the memsets then run beside the forward recurrence (which leaves 20 SMs and
+// most of the HBM bandwidth idle) instead of in front of it.  The backward half waits for ev_zero.
+static void zero_behind_projection(hpmn_ctx* ctx, cudaStream_t st) {
+  if (!ctx->zero_grads && !ctx->zero_late) return;
+  cudaEventRecord(ctx->ev_fork[HPMN_MAX_LAYERS + 1], st);
+  cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS + 1], 0);
+  Launch L{&ctx->launches, ctx->sms};
+  static const int zctas = [] { const char* e = getenv("HPMN_ZERO_CTAS"); return e ? atoi(e) : 0; }();
+  // with the wavefront kernel on 128 SMs a grid of 2 CTAs per idle SM; otherwise whatever cudaMemsetAsync launches
+  const int ctas = zctas > 0 ? zctas : (ctx->wave_now ? 2 * (ctx->sms > 128 ? ctx->sms - 128 : 8) : 0);
+  if (ctx->zero_grads) cudaMemsetAsync(ctx->zero_grads, 0, ctx->zero_grads_bytes, ctx->side);
+  if (ctx->zero_late) {
+    if (ctas > 0) launch_zero(L, ctx->zero_late, ctx->zero_late_bytes, ctas, ctx->side);
+    else cudaMemsetAsync(ctx->zero_late, 0, ctx->zero_late_bytes, ctx->side);
+  }
+  cudaEventRecord(ctx->ev_zero, ctx->side);
+  ctx->zero_pending = true;
+  ctx->zero_grads = nullptr; ctx->zero_late = nullptr;
+}
+
 static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const float* params, float* memory,
                            cudaStream_t st, bool packed = false) {
   Launch L{&ctx->launches, ctx->sms};
@@ -316,6 +338,7 @@ static void run_memory_fwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
     // layer-0 input projections (dense, tensor cores), then every layer of every sample as one wavefront kernel
     { Bracket b(ctx, st, HPMN_K_INPROJ);
       dense_gemm(ctx, L, x, d.D, pw + p.pk.Wx[0], pw + p.pk.bx[0], p.f(p.wl.proj[0]), (int64_t)d.B * d.S[0], G3, d.DinP[0], st); }
+    zero_behind_projection(ctx, st);
     float* stp[HPMN_MAX_LAYERS];
     for (int k = 0; k < d.L; ++k) stp[k] = p.f(p.wl.st[k]);
     Bracket b(ctx, st, HPMN_K_REC_FWD);
@@ -440,6 +463,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   cudaEventCreateWithFlags(&ctx->ev_dtable, cudaEventDisableTiming);
   ctx->comm = nullptr;
   ctx->zero_pending = false;
+  ctx->zero_late = nullptr; ctx->zero_grads = nullptr; ctx->zero_late_bytes = 0; ctx->zero_grads_bytes = 0;
   cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   for (auto& ev : ctx->ev_consumed) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -675,6 +699,7 @@ static void fwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   if (ov) cudaStreamWaitEvent(st, ctx->ev_join, 0);
   if (!(ctx->tc_now && run_memory_fwd_tc(ctx, p, x, params, memory, st, ov)))
     run_memory_fwd(ctx, p, x, params, memory, st, ov);
+  zero_behind_projection(ctx, st);     // no-op when run_memory_fwd already queued it behind the projection GEMM
   if (ctx->fuse_now) return;    // bwd_rows runs attention + head, both directions, as one kernel
   { Bracket b(ctx, st, HPMN_K_ATTN_FWD);
     launch_attn_fwd(L, d, p.pl, s->last_offset, memory, x, params, p.f(p.wl.repre), p.hf(p.hdr.w_hop0) + (int64_t)r0 * d.L,
@@ -731,6 +756,7 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
   };
   if (tc) {
     // tensor-core recurrence: everything on `st` (its dense kernels fill the machine at the batch sizes that select it)
+    if (ctx->zero_pending) { cudaStreamWaitEvent(st, ctx->ev_zero, 0); ctx->zero_pending = false; }   // grads are written on `st`
     run_memory_bwd_tc(ctx, p, x, params, p.f(p.wl.dmemory), dx0, grads, st, true);
     scatter();
   } else {
@@ -742,7 +768,7 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
 // One step: prologue on `st`, G concurrent row-group chains, epilogue on `st`.  scalars: device float[4].
 static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hyper hy, const int32_t* ids, const int32_t* labels,
                     const float* params, const float* table, float* grads, float* dtable, int zero_dtable, bool with_backward,
-                    float* scalars, cudaStream_t st) {
+                    float* scalars, cudaStream_t st, const hpmn_outputs* out_dev = nullptr) {
   Launch L{&ctx->launches, ctx->sms};
   const Dims& d = p.d;
   if (d.H > HP && !tcrec_supported(d))
@@ -771,22 +797,19 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
     launch_pack(L, d, p.pl, p.pk, params, p.f(p.wl.pw), ctx->side);
     CK(cudaEventRecord(ctx->ev_join, ctx->side));
   }
+  ctx->zero_late = nullptr; ctx->zero_late_bytes = 0; ctx->zero_grads = nullptr; ctx->zero_grads_bytes = 0;
   { Bracket b(ctx, st, HPMN_K_MISC);
     CK(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
     if (with_backward) {
-      CK(cudaMemsetAsync(grads, 0, (size_t)p.pl.total * sizeof(float), st));
-      if (zero_dtable) {
-        if (G == 1 && ctx->overlap && !ctx->profile) {
-          // the table gradient is only touched by the scatter at the very end: zero its 212 MB on the side stream, behind
-          // the forward pass, and make the scatter wait for it
-          CK(cudaEventRecord(ctx->ev_fork[HPMN_MAX_LAYERS + 1], st));
-          CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS + 1], 0));
-          CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), ctx->side));
-          CK(cudaEventRecord(ctx->ev_zero, ctx->side));
-          ctx->zero_pending = true;
-        } else {
-          CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st));
-        }
+      if (G == 1 && ctx->overlap && !ctx->profile) {
+        // Neither gradient buffer is touched before the backward half: both are zeroed on the side stream once the forward
+        // recurrence is under way (fwd_rows -> zero_behind_projection).  At the head of the step the 212 MB memset held
+        // every SM while the projection GEMM was ready to run: 22 us of the critical path (tools/timeline.py).
+        ctx->zero_grads = grads; ctx->zero_grads_bytes = (size_t)p.pl.total * sizeof(float);
+        if (zero_dtable) { ctx->zero_late = dtable; ctx->zero_late_bytes = (size_t)s->V * d.E * sizeof(float); }
+      } else {
+        CK(cudaMemsetAsync(grads, 0, (size_t)p.pl.total * sizeof(float), st));
+        if (zero_dtable) CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st));
       }
     } }
   if (G == 1) {
@@ -809,7 +832,16 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
     }
   }
   { Bracket b(ctx, st, HPMN_K_MISC);
-    launch_finish_scalars(L, scalars, hy.memory_reg, st);
+    OutCopies oc; memset(&oc, 0, sizeof(oc));
+    if (out_dev) {       // the caller's device buffers are filled by the same launch (no cudaMemcpyAsync per output)
+      int n = 0;
+      auto add = [&](float* dst, const float* src, int64_t cnt) { if (dst) { oc.dst[n] = dst; oc.src[n] = src; oc.n[n] = cnt; ++n; } };
+      add(out_dev->pred, p.hf(p.hdr.pred), d.B);
+      add(out_dev->logit, p.hf(p.hdr.logit), d.B);
+      add(out_dev->w_hop0, p.hf(p.hdr.w_hop0), (int64_t)d.B * d.L);
+      add(out_dev->memory, p.hf(p.hdr.memory), (int64_t)d.B * d.L * d.H);
+    }
+    launch_finish_scalars(L, scalars, hy.memory_reg, out_dev ? &oc : nullptr, st);
     if (hy.l2_reg != 0.f) {   // l2_reg * tf.nn.l2_loss(v) over every trainable, code/hpmn.py:204-205
       // Under data parallelism every rank holds the same parameters and the gradients / scalars are SUMMED over ranks:
       // each rank contributes its share B / loss_batch of the (batch-independent) l2 term, so the sum is exactly one l2 term.
@@ -846,9 +878,7 @@ int hpmn_forward(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* hy, const
   if (!ids || !labels || !params || !table || !out || !out->scalars) return fail(ctx, HPMN_EINVAL, "NULL buffer");
   hpmn_hyper h = hy ? *hy : default_hyper();
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_step(ctx, p, s, h, ids, labels, params, table, nullptr, nullptr, 0, false, out->scalars, st);
-  if (rc) return rc;
-  rc = copy_outputs(ctx, p, out, cudaMemcpyDeviceToDevice, st);
+  rc = run_step(ctx, p, s, h, ids, labels, params, table, nullptr, nullptr, 0, false, out->scalars, st, out);
   if (rc) return rc;
   return check_launch(ctx, "hpmn_forward");
 }
@@ -862,9 +892,7 @@ int hpmn_forward_backward(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* 
     return fail(ctx, HPMN_EINVAL, "NULL buffer");
   hpmn_hyper h = hy ? *hy : default_hyper();
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_step(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, true, out->scalars, st);
-  if (rc) return rc;
-  rc = copy_outputs(ctx, p, out, cudaMemcpyDeviceToDevice, st);
+  rc = run_step(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, true, out->scalars, st, out);
   if (rc) return rc;
   return check_launch(ctx, "hpmn_forward_backward");
 }

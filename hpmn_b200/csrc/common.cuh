@@ -445,7 +445,11 @@ void launch_nvls_allreduce(const Launch&, float* mc, int64_t n_floats, int rank,
 void launch_clip_adam(const Launch&, float* var, const float* grad, float* m, float* v, int64_t n, float lr_t, float b1,
                       float b2, float eps, float clip, cudaStream_t st);
 void launch_axpy(const Launch&, float* y, const float* x, float a, int64_t n, cudaStream_t st);
-void launch_finish_scalars(const Launch&, float* scalars, float memory_reg, cudaStream_t st);
+// loss = logloss + memory_reg * covreg, and (optionally) the per-row results copied from the workspace staging to the caller's
+// device buffers by the same launch (four device-to-device copies cost ~16 us of stream time at the end of every step)
+void launch_zero(const Launch&, void* ptr, size_t bytes, int ctas, cudaStream_t st);
+struct OutCopies { const float* src[4]; float* dst[4]; int64_t n[4]; };
+void launch_finish_scalars(const Launch&, float* scalars, float memory_reg, const OutCopies* copies, cudaStream_t st);
 
 // dropout keep-mask shared by head fwd/bwd (counter-based hash; deterministic in seed, sample, unit)
 #ifdef __CUDACC__

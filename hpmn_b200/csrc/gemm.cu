@@ -335,12 +335,39 @@ void launch_axpy(const Launch& L, float* y, const float* x, float a, int64_t n, 
   ++*L.counter;
 }
 
-// loss = logloss + memory_reg * covreg   (code/hpmn.py:202-207; the l2 term is added by the caller)
-__global__ void finish_scalars_kernel(float* s, float memory_reg) {
-  s[HPMN_S_LOSS] = s[HPMN_S_LOGLOSS] + memory_reg * s[HPMN_S_COVREG];
+// Zeroing that is meant to run BESIDE the forward recurrence: a small fixed grid (the wavefront kernel leaves 20 SMs idle;
+// cudaMemsetAsync would launch a machine-wide grid that the block scheduler serialises against the kernels around it).
+__global__ void __launch_bounds__(512) zero_kernel(float4* p4, int64_t n4, float* tail, int ntail) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p4[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
-void launch_finish_scalars(const Launch& L, float* scalars, float memory_reg, cudaStream_t st) {
-  finish_scalars_kernel<<<1, 1, 0, st>>>(scalars, memory_reg);
+void launch_zero(const Launch& L, void* ptr, size_t bytes, int ctas, cudaStream_t st) {
+  if (!ptr || bytes == 0) return;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (bytes & 3)) { cudaMemsetAsync(ptr, 0, bytes, st); return; }
+  const int64_t n4 = (int64_t)(bytes / 16);
+  const int ntail = (int)((bytes % 16) / 4);
+  zero_kernel<<<ctas < 1 ? 1 : ctas, 512, 0, st>>>(reinterpret_cast<float4*>(ptr), n4, reinterpret_cast<float*>(ptr) + n4 * 4, ntail);
+  ++*L.counter;
+}
+
+// loss = logloss + memory_reg * covreg   (code/hpmn.py:202-207; the l2 term is added by the caller)
+__global__ void finish_scalars_kernel(float* s, float memory_reg, const __grid_constant__ OutCopies c) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) s[HPMN_S_LOSS] = s[HPMN_S_LOGLOSS] + memory_reg * s[HPMN_S_COVREG];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    for (int64_t i = i0; i < c.n[k]; i += stride) c.dst[k][i] = c.src[k][i];
+}
+void launch_finish_scalars(const Launch& L, float* scalars, float memory_reg, const OutCopies* copies, cudaStream_t st) {
+  OutCopies c; memset(&c, 0, sizeof(c));
+  int64_t total = 0;
+  if (copies) { c = *copies; for (int k = 0; k < 4; ++k) total += c.n[k]; }
+  int64_t blocks = (total + 1023) / 1024;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (int64_t)L.sms * 4) blocks = (int64_t)L.sms * 4;
+  finish_scalars_kernel<<<(int)blocks, 256, 0, st>>>(scalars, memory_reg, c);
   ++*L.counter;
 }
 

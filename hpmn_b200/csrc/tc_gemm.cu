@@ -221,7 +221,7 @@ tc_gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
 // ---------------------------------------------------------------------------------------------------
 constexpr int WK = 32;                 // rows per stage (= MMA K per stage)
 #ifndef HPMN_WNS
-#define HPMN_WNS 3
+#define HPMN_WNS 3      // default number of stages (wgrad_stages())
 #endif
 constexpr int WNS = HPMN_WNS;          // stages
 constexpr int WCHS_A = 128 * 16 + 16;  // bytes between 4-row K chunks of the feature tile (padded)
@@ -262,7 +262,7 @@ struct WgradProb {
 };
 struct WgradBatch { int n, H, producer_fence, pad_; WgradProb p[HPMN_MAX_LAYERS]; };
 
-template <int DINP>
+template <int DINP, int NS>
 __global__ void __launch_bounds__(32 * (WPW + 1))
 tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   static_assert(DINP + 64 < 128, "the ones row needs a free feature slot");
@@ -279,9 +279,9 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   constexpr int NX = (NXU + WPW - 1) / WPW;
   constexpr uint32_t IDESC = umma_idesc_tf32(128, 96, 0, 0);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + WNS * W_STAGE);
-  uint64_t* empty = full + WNS;
-  uint64_t* done = empty + WNS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * W_STAGE);
+  uint64_t* empty = full + NS;
+  uint64_t* done = empty + NS;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t mbeg = (int64_t)cta * rows_per_cta;
@@ -290,12 +290,12 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
 
   if (warp == WPW) tmem_alloc(tslot, 128);
   if (tid == 0) {
-    for (int i = 0; i < WNS; ++i) { mbar_init(&full[i], 32 * WPW); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 32 * WPW); mbar_init(&empty[i], 1); }
     mbar_init(done, 1);
     fence_mbar_init();
   }
   // pad features [DINP+64, 128): zeros, except feature 127 = 1.0 (hi part) -> bias gradients
-  for (int e = tid; e < WNS * (64 - DINP) * WK; e += 32 * (WPW + 1)) {
+  for (int e = tid; e < NS * (64 - DINP) * WK; e += 32 * (WPW + 1)) {
     const int stg = e / ((64 - DINP) * WK), r = e % ((64 - DINP) * WK);
     const int feat = DINP + 64 + r / WK, k = r % WK;
     unsigned char* base = smem_raw + stg * W_STAGE;
@@ -355,8 +355,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
       while (hrem >= S) hrem -= S;
     };
     auto store = [&](const Regs& R, int sidx) {
-      const int slot = sidx % WNS;
-      if (sidx >= WNS) mbar_wait(&empty[slot], (uint32_t)((sidx / WNS) - 1) & 1u);     // MMAs that read this slot are done
+      const int slot = sidx % NS;
+      if (sidx >= NS) mbar_wait(&empty[slot], (uint32_t)((sidx / NS) - 1) & 1u);     // MMAs that read this slot are done
       unsigned char* base = smem_raw + slot * W_STAGE;
       unsigned char* At_hi = base;
       unsigned char* At_lo = base + W_AT;
@@ -434,8 +434,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
     // ================= MMA warp =================
     if (lane == 0) {
       for (int sidx = 0; sidx < nst; ++sidx) {
-        const int slot = sidx % WNS;
-        mbar_wait(&full[slot], (uint32_t)(sidx / WNS) & 1u);
+        const int slot = sidx % NS;
+        mbar_wait(&full[slot], (uint32_t)(sidx / NS) & 1u);
         fence_proxy_async();                  // producers' generic-proxy stores (ordered by the barrier) -> async proxy
         tc_fence_after();
         const uint32_t base = smem_u32(smem_raw + slot * W_STAGE);
@@ -484,6 +484,28 @@ static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin,
   ctas += n;
 }
 
+// Stages of the producer -> MMA ring and the shared-memory carve-out the kernel asks for.  Default: 2 stages (116 KB) and the
+// smallest carve-out that holds them, which leaves ~124 KB of the SM's unified array to L1 -- the producers' row loads
+// (x, h, r, dA rows are each read by several warps) hit there.  Measured on the XLong step: 3 stages / driver-chosen split
+// 121 us, 3 stages / maximal carve-out 162 us, 2 stages / minimal carve-out 117 us.  HPMN_WGRAD_STAGES=3 and
+// HPMN_WGRAD_CARVEOUT=<percent, -1 = driver default> override.
+static int wgrad_stages() {
+  static const int ns = [] { const char* e = getenv("HPMN_WGRAD_STAGES"); const int v = e ? atoi(e) : 2; return v == 3 ? 3 : 2; }();
+  return ns;
+}
+template <int DINP>
+static void wgrad_go(int ctas, cudaStream_t st, const WgradBatch& b) {
+  static const int carve = [] { const char* e = getenv("HPMN_WGRAD_CARVEOUT"); return e ? atoi(e) : 50; }();
+  const int ns = wgrad_stages();
+  const size_t smem = (size_t)ns * W_STAGE + 128;
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (carve >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    kern<<<ctas, 32 * (WPW + 1), smem, st>>>(b);
+  };
+  if (ns == 2) go(tc_wgrad_kernel<DINP, 2>); else go(tc_wgrad_kernel<DINP, 3>);
+}
+
 // H = 64 (layouts of tcrec.cu: state rows [h|r|u|c] x 64, dA rows [r|u|c] x 64).  The kernel's tile is [x (32|48) | h (32) | r*h (32) |
 // ones] x [r|u|c] (3 x 32), so a layer is cut into slices: hidden rows 32a.. against gate columns 32bq..; the x rows and the bias
 // row are taken from the a = 0 slices; the layers above layer 0 have 64 input rows and get one more pair of slices for inputs [32,64).
@@ -493,7 +515,6 @@ bool launch_tc_wgrad_wide(const Launch& L, const Dims& d, const float* const* xi
   if (d.H != 64) return false;
   const int dp0 = ((d.D + 15) / 16) * 16;
   if (dp0 != 32 && dp0 != 48) return false;
-  const size_t smem = (size_t)WNS * W_STAGE + 128;
   for (int pass = 0; pass < 2; ++pass) {          // pass 0: layer 0 (tile with 32 or 48 x rows); pass 1: the layers above (32 x rows)
     for (int k0 = pass == 0 ? 0 : 1; k0 < (pass == 0 ? 1 : d.L); k0 += 2) {      // at most 2 layers (12 slices) per launch
       WgradBatch b; b.n = 0; b.H = 32; b.producer_fence = wgrad_producer_fence();
@@ -519,11 +540,9 @@ bool launch_tc_wgrad_wide(const Launch& L, const Dims& d, const float* const* xi
           }
       }
       if (pass == 0 && dp0 == 48) {
-        cudaFuncSetAttribute(tc_wgrad_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc_wgrad_kernel<48><<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
+        wgrad_go<48>(ctas, st_, b);
       } else {
-        cudaFuncSetAttribute(tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc_wgrad_kernel<32><<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
+        wgrad_go<32>(ctas, st_, b);
       }
       ++*L.counter;
     }
@@ -546,15 +565,12 @@ bool launch_tc_wgrad_all(const Launch& L, const Dims& d, const float* const* xin
     if (d.DinP[k] == 32) wgrad_queue_add(b32, c32, L.sms, xin[k], ldx[k], st[k], da[k], dWg[k], dbg[k], dWc[k], dbc[k], M, d.S[k], d.Din[k], rows32);
     else wgrad_queue_add(b48, c48, L.sms, xin[k], ldx[k], st[k], da[k], dWg[k], dbg[k], dWc[k], dbc[k], M, d.S[k], d.Din[k], rows48);
   }
-  const size_t smem = (size_t)WNS * W_STAGE + 128;
   if (b48.n) {
-    cudaFuncSetAttribute(tc_wgrad_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tc_wgrad_kernel<48><<<c48, 32 * (WPW + 1), smem, st_>>>(b48);
+    wgrad_go<48>(c48, st_, b48);
     ++*L.counter;
   }
   if (b32.n) {
-    cudaFuncSetAttribute(tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tc_wgrad_kernel<32><<<c32, 32 * (WPW + 1), smem, st_>>>(b32);
+    wgrad_go<32>(c32, st_, b32);
     ++*L.counter;
   }
   return true;
@@ -568,12 +584,7 @@ bool launch_tc_wgrad(const Launch& L, const Dims& d, int k, const float* xin, in
   int ctas = 0;
   const int64_t M = (int64_t)d.B * d.S[k];
   wgrad_queue_add(b, ctas, L.sms, xin, ldx, st, da, dWg, dbg, dWc, dbc, M, d.S[k], d.Din[k], M);
-  const size_t smem = (size_t)WNS * W_STAGE + 128;
-  auto go = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<ctas, 32 * (WPW + 1), smem, st_>>>(b);
-  };
-  if (DinP == 32) go(tc_wgrad_kernel<32>); else go(tc_wgrad_kernel<48>);
+  if (DinP == 32) wgrad_go<32>(ctas, st_, b); else wgrad_go<48>(ctas, st_, b);
   ++*L.counter;
   return true;
 }
