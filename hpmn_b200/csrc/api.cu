@@ -36,6 +36,8 @@ struct hpmn_ctx {
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
   void* zero_late; size_t zero_late_bytes; void* zero_grads; size_t zero_grads_bytes;   // buffers zero_behind_projection() clears
+  void* fin_d2h_dst; size_t fin_d2h_bytes; cudaEvent_t fin_d2h_ev; bool fin_d2h_done;   // host path: result block copied out early
+  OutCopies fin_oc; float* fin_scalars; float fin_mreg; bool fin_copies, fin_early;   // the step's finish kernel (see run_step)
   bool fuse_mid;            // training step: attention + head, forward and backward, as one kernel (mid.cu); HPMN_NO_FUSE_MID=1 disables
   bool fuse_now;            // ... for the step being queued
   bool dtable_late;         // this step touches dtable after the scatter of the whole-batch chain (row groups, l2 term)
@@ -464,6 +466,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx->comm = nullptr;
   ctx->zero_pending = false;
   ctx->zero_late = nullptr; ctx->zero_grads = nullptr; ctx->zero_late_bytes = 0; ctx->zero_grads_bytes = 0;
+  ctx->fin_d2h_dst = nullptr; ctx->fin_d2h_done = false; ctx->fin_early = false;
   cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   for (auto& ev : ctx->ev_consumed) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -739,6 +742,16 @@ static void bwd_rows(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, const hp
       cudaEventRecord(ctx->ev_fork[HPMN_MAX_LAYERS], st);
       cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS], 0);
       launch_atb_batch(L, batch, ctx->side);
+      if (ctx->fin_early) {    // loss + output copies only need what the attention / head section produced: off the critical path
+        launch_finish_scalars(L, ctx->fin_scalars, ctx->fin_mreg, ctx->fin_copies ? &ctx->fin_oc : nullptr, ctx->side);
+        ctx->fin_early = false;
+        if (ctx->fin_d2h_dst) {   // host path: the result block (scalars | pred | logit | w_hop0) is final here -- the host gets it
+                                  // while the backward recurrence runs instead of behind a D2H at the end of the step
+          cudaMemcpyAsync(ctx->fin_d2h_dst, ctx->fin_scalars, ctx->fin_d2h_bytes, cudaMemcpyDeviceToHost, ctx->side);
+          cudaEventRecord(ctx->fin_d2h_ev, ctx->side);
+          ctx->fin_d2h_done = true;
+        }
+      }
     } else {
       launch_atb_batch(L, batch, st);
     } }
@@ -812,6 +825,22 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
         if (zero_dtable) CK(cudaMemsetAsync(dtable, 0, (size_t)s->V * d.E * sizeof(float), st));
       }
     } }
+  // The finish kernel (loss = logloss + memory_reg * covreg, and the per-row results copied to the caller's device buffers: one
+  // launch instead of a cudaMemcpyAsync per output) needs nothing the backward recurrence produces: in the training step it
+  // goes to the side stream behind the attention / head weight gradients (bwd_rows) and is joined with them.
+  memset(&ctx->fin_oc, 0, sizeof(ctx->fin_oc));
+  if (out_dev) {
+    int n = 0;
+    auto add = [&](float* dst, const float* src, int64_t cnt) {
+      if (dst) { ctx->fin_oc.dst[n] = dst; ctx->fin_oc.src[n] = src; ctx->fin_oc.n[n] = cnt; ++n; } };
+    add(out_dev->pred, p.hf(p.hdr.pred), d.B);
+    add(out_dev->logit, p.hf(p.hdr.logit), d.B);
+    add(out_dev->w_hop0, p.hf(p.hdr.w_hop0), (int64_t)d.B * d.L);
+    add(out_dev->memory, p.hf(p.hdr.memory), (int64_t)d.B * d.L * d.H);
+  }
+  ctx->fin_scalars = scalars; ctx->fin_mreg = hy.memory_reg; ctx->fin_copies = out_dev != nullptr;
+  const bool fin_on_side = with_backward && G == 1 && ctx->overlap && !ctx->profile && hy.l2_reg == 0.f;
+  ctx->fin_early = fin_on_side;
   if (G == 1) {
     fwd_rows(ctx, p, s, hy, ids, labels, params, table, scalars, side_pack, st);
     if (with_backward) bwd_rows(ctx, p, s, hy, ids, labels, params, grads, dtable, scalars, true, st);
@@ -832,16 +861,7 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
     }
   }
   { Bracket b(ctx, st, HPMN_K_MISC);
-    OutCopies oc; memset(&oc, 0, sizeof(oc));
-    if (out_dev) {       // the caller's device buffers are filled by the same launch (no cudaMemcpyAsync per output)
-      int n = 0;
-      auto add = [&](float* dst, const float* src, int64_t cnt) { if (dst) { oc.dst[n] = dst; oc.src[n] = src; oc.n[n] = cnt; ++n; } };
-      add(out_dev->pred, p.hf(p.hdr.pred), d.B);
-      add(out_dev->logit, p.hf(p.hdr.logit), d.B);
-      add(out_dev->w_hop0, p.hf(p.hdr.w_hop0), (int64_t)d.B * d.L);
-      add(out_dev->memory, p.hf(p.hdr.memory), (int64_t)d.B * d.L * d.H);
-    }
-    launch_finish_scalars(L, scalars, hy.memory_reg, out_dev ? &oc : nullptr, st);
+    if (!fin_on_side) launch_finish_scalars(L, scalars, hy.memory_reg, out_dev ? &ctx->fin_oc : nullptr, st);
     if (hy.l2_reg != 0.f) {   // l2_reg * tf.nn.l2_loss(v) over every trainable, code/hpmn.py:204-205
       // Under data parallelism every rank holds the same parameters and the gradients / scalars are SUMMED over ranks:
       // each rank contributes its share B / loss_batch of the (batch-independent) l2 term, so the sum is exactly one l2 term.
@@ -926,29 +946,34 @@ int hpmn_step_host_begin(hpmn_ctx* ctx, const hpmn_shape* s, const hpmn_hyper* h
     CK(cudaMemcpyAsync(labels, labels_host, (size_t)d.B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
   ctx->cur_slot = slot;
+  const char* hb = reinterpret_cast<const char*>(oh->scalars);
+  const bool mirrored = oh->pred && oh->logit && oh->w_hop0 && !oh->memory &&
+                        reinterpret_cast<const char*>(oh->pred) - hb == (ptrdiff_t)(p.hdr.pred - p.hdr.scalars) &&
+                        reinterpret_cast<const char*>(oh->logit) - hb == (ptrdiff_t)(p.hdr.logit - p.hdr.scalars) &&
+                        reinterpret_cast<const char*>(oh->w_hop0) - hb == (ptrdiff_t)(p.hdr.w_hop0 - p.hdr.scalars);
+  const int k = ctx->out_next; ctx->out_next ^= 1;     // hpmn_step_host_end(oh) waits for ev_out[k]
+  // a host caller whose result buffers mirror the staging block gets ONE D2H copy per step; in the training step run_step
+  // issues it on the side stream as soon as the block is final (behind the attention / head section)
+  ctx->fin_d2h_dst = mirrored ? oh->scalars : nullptr;
+  ctx->fin_d2h_bytes = p.hdr.out_end - p.hdr.scalars;
+  ctx->fin_d2h_ev = ctx->ev_out[k];
+  ctx->fin_d2h_done = false;
   rc = run_step(ctx, p, s, h, ids, labels, params, table, grads, dtable, zero_dtable, with_backward != 0, scalars, st);
+  ctx->fin_d2h_dst = nullptr;
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev_consumed[slot], st));       // the slot may be refilled once everything above has read it
   ctx->consumed_valid[slot] = true;
-  {
-    const char* hb = reinterpret_cast<const char*>(oh->scalars);
-    const bool mirrored = oh->pred && oh->logit && oh->w_hop0 && !oh->memory &&
-                          reinterpret_cast<const char*>(oh->pred) - hb == (ptrdiff_t)(p.hdr.pred - p.hdr.scalars) &&
-                          reinterpret_cast<const char*>(oh->logit) - hb == (ptrdiff_t)(p.hdr.logit - p.hdr.scalars) &&
-                          reinterpret_cast<const char*>(oh->w_hop0) - hb == (ptrdiff_t)(p.hdr.w_hop0 - p.hdr.scalars);
-    if (mirrored) {          // the host result buffers mirror the staging block (hpmn_output_block): one copy instead of four
+  if (!ctx->fin_d2h_done) {
+    if (mirrored) {
       CK(cudaMemcpyAsync(oh->scalars, scalars, p.hdr.out_end - p.hdr.scalars, cudaMemcpyDeviceToHost, st));
     } else {
       CK(cudaMemcpyAsync(oh->scalars, scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
       rc = copy_outputs(ctx, p, oh, cudaMemcpyDeviceToHost, st);
       if (rc) return rc;
     }
-  }
-  { // hpmn_step_host_end(oh) waits for exactly this point, so that the NEXT step may already be queued behind it
-    const int k = ctx->out_next; ctx->out_next ^= 1;
     CK(cudaEventRecord(ctx->ev_out[k], st));
-    ctx->out_key[k] = oh->scalars;
   }
+  ctx->out_key[k] = oh->scalars;
   return check_launch(ctx, "hpmn_step_host");
 }
 

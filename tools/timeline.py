@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/timeline.txt")
+    ap.add_argument("--host", action="store_true", help="the host-buffer path (hpmn_step_host_begin / _end, two steps in flight)")
     args = ap.parse_args()
     cfg = bench.CONFIGS["xlong"]
     B = args.batch or cfg["batch"]
@@ -40,12 +41,24 @@ def main():
     def step(i):
         eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=0.5, seed=i, loss_batch=B)
 
+    h_ids = [t.cpu().pin_memory() for t in d_ids]
+    h_lab = [t.cpu().pin_memory() for t in d_lab]
+
+    def host_steps(n):
+        feeds = ((h_ids[i % NB], h_lab[i % NB]) for i in range(n))
+        for _ in eng.step_host_stream(feeds, True, 0.5, seed0=1, loss_batch=B):
+            pass
+
     for i in range(8):
         step(i)
+    host_steps(4)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        for i in range(args.steps):
-            step(i)
+        if args.host:
+            host_steps(args.steps)
+        else:
+            for i in range(args.steps):
+                step(i)
         torch.cuda.synchronize()
     tmp = tempfile.mktemp(suffix=".json")
     prof.export_chrome_trace(tmp)
