@@ -380,6 +380,17 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
       { Bracket b(ctx, st, HPMN_K_DX);
         dense_gemm(ctx, L, dap[0], G3, pw + p.pk.WxT[0], nullptr, dx0, (int64_t)d.B * d.S[0], d.DinP[0], G3, st); }
       if (after_dx) after_dx();
+      // A collective stream is attached (multi-GPU): the table gradient must be final as early as possible and the exchange
+      // kernels need SMs while the weight gradients are reduced.  Left alone, the persistent weight-gradient grid takes every
+      // SM the moment the dX GEMM drains and the scatter waits 117 us behind it (tools/timeline.py).  So the weight-gradient
+      // kernel is ordered behind the scatter and leaves HPMN_COMM_SMS (default 24) SMs to the exchange.
+      Launch Lw = L;
+      if (ov && ctx->comm && after_dx) {
+        static const int reserve = [] { const char* e = getenv("HPMN_COMM_SMS"); return e ? atoi(e) : 24; }();
+        cudaEventRecord(ctx->ev_fork[1], st);
+        cudaStreamWaitEvent(ctx->side, ctx->ev_fork[1], 0);
+        if (reserve > 0 && reserve < ctx->sms - 16) Lw.sms = ctx->sms - reserve;
+      }
       { Bracket b(ctx, st, HPMN_K_WGRAD);
         const float* xa[HPMN_MAX_LAYERS]; int64_t lx[HPMN_MAX_LAYERS];
         float *gWg[HPMN_MAX_LAYERS], *gbg[HPMN_MAX_LAYERS], *gWc[HPMN_MAX_LAYERS], *gbc[HPMN_MAX_LAYERS];
@@ -388,7 +399,7 @@ static void run_memory_bwd(hpmn_ctx* ctx, const Plan& p, const float* x, const f
           lx[k] = k == 0 ? d.D : (int64_t)d.P[k - 1] * ST;
           gWg[k] = grads + p.pl.Wg[k]; gbg[k] = grads + p.pl.bg[k]; gWc[k] = grads + p.pl.Wc[k]; gbc[k] = grads + p.pl.bc[k];
         }
-        if (!(ctx->use_tc && launch_tc_wgrad_all(L, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, ws)))
+        if (!(ctx->use_tc && launch_tc_wgrad_all(Lw, d, xa, lx, stp, dap, gWg, gbg, gWc, gbc, ws)))
           for (int k = 0; k < d.L; ++k)
             launch_gru_wgrad(L, d, k, xa[k], lx[k], stp[k], dap[k], gWg[k], gbg[k], gWc[k], gbc[k], ws);
       }

@@ -32,14 +32,20 @@ def main():
     B = args.batch or cfg["batch"]
     sh = HpmnShape(B=B, T=cfg["T"], F=cfg["F"], E=cfg["E"], H=cfg["H"], periods=cfg["periods"], L=cfg["L"], hops=cfg["hops"],
                    V=cfg["V"], front_pad=cfg["front_pad"], mask_id0=cfg["mask_id0"], last_offset=cfg["last_offset"])
-    eng = HpmnEngine(sh, device=0, memory_reg=cfg["memory_reg"], seed=4321)
+    from hpmn_b200 import dist as hd
+    rank, local_rank, world = hd.init_process_group("nccl")      # torchrun: one rank per GPU, the step includes the exchange
+    eng = HpmnEngine(sh, device=local_rank, memory_reg=cfg["memory_reg"], seed=4321, symmetric=world > 1)
+    if world > 1:
+        hd.GradExchange(eng, mode=os.environ.get("HPMN_EXCHANGE", "auto")).attach()
     dev = eng.device
     NB = 4
-    d_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + i)).to(dev) for i in range(NB)]
+    d_ids = [torch.from_numpy(synthetic_ids(B, sh.T, sh.F, sh.V, seed=1234 + 97 * rank + i)).to(dev) for i in range(NB)]
     d_lab = [torch.from_numpy(np.random.default_rng(99 + i).integers(0, 2, size=B).astype(np.int32)).to(dev) for i in range(NB)]
 
     def step(i):
-        eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=0.5, seed=i, loss_batch=B)
+        eng.forward_backward(d_ids[i % NB], d_lab[i % NB], keep_prob=0.5, seed=i * world + rank, loss_batch=B * world)
+        if world > 1:
+            hd.exchange_grads(eng)
 
     h_ids = [t.cpu().pin_memory() for t in d_ids]
     h_lab = [t.cpu().pin_memory() for t in d_lab]
@@ -81,9 +87,13 @@ def main():
         name = e["name"].replace("hpmn::", "").split("(")[0][:46]
         lines.append("%-46s %7s %9.1f %9.1f %8.1f %8.1f" % (name, st, s, s + d, d, gap))
     lines.append("step period (gather to gather): %.1f us" % (ev[hi]["ts"] - ev[gathers[-2]]["ts"]))
-    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
-    open(args.out, "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines))
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        open(args.out, "w").write("\n".join(lines) + "\n")
+        print("\n".join(lines))
+    if world > 1:
+        hd.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
