@@ -14,3 +14,5 @@ except Exception as e:
     print("N=$N $m failed", e); print(open("gpurun_out/r2_n${N}_$m.err").read()[-1200:])
 PY
 done
+# rank-0 kernel timeline of the step incl. the exchange (tools/timeline.py under torchrun)
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 tools/timeline.py --out gpurun_out/timeline_n$N.txt 2>/dev/null | tail -16
