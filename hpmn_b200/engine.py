@@ -202,7 +202,8 @@ class HpmnEngine:
 
     def step_host(self, ids: np.ndarray, labels: np.ndarray, with_backward: bool = True, keep_prob: float = 1.0,
                   seed: int = 0, loss_batch: int = 0, zero_dtable: bool = True):
-        """Host buffers in, host results out (pinned staging, H2D + compute + D2H + stream sync inside)."""
+        """Host buffers in, host results out (pinned staging; H2D + compute + D2H inside; returns when the host results have
+        landed -- the gradient buffers are device tensors and complete in stream order on the current stream)."""
         B = int(np.shape(ids)[0])
         self.h_ids.numpy().reshape(-1)[: B * self.shape.T * self.shape.F] = np.asarray(ids, dtype=np.int32).reshape(-1)
         self.h_labels.numpy()[:B] = np.asarray(labels, dtype=np.int32)

@@ -178,7 +178,11 @@ int hpmn_step_host(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_
 /* The same call split in two so that other work can be queued between enqueue and wait: _begin enqueues H2D + compute +
  * D2H and returns immediately, _end waits until the results of THAT step (identified by out_host->scalars) have landed in host
  * memory and reports an out-of-range id.  Up to two steps may be in flight when they use distinct out_host buffers: _begin of
- * step i+1 may be called before _end of step i, so the host's enqueue time of step i+1 hides behind the device time of step i. */
+ * step i+1 may be called before _end of step i, so the host's enqueue time of step i+1 hides behind the device time of step i.
+ * _end returns when the HOST results are there -- in the training step (with_backward, mirrored result block, l2_reg = 0) that is
+ * as soon as the attention / head section has run, i.e. before the backward recurrence has finished.  The gradient buffers
+ * (grads, dtable) are device memory and complete in stream order on `stream`, like after hpmn_forward_backward: anything queued
+ * on `stream` afterwards sees them; a host read needs a stream synchronisation. */
 int hpmn_step_host_begin(hpmn_ctx*, const hpmn_shape*, const hpmn_hyper*, const int32_t* ids_host,
                          const int32_t* labels_host, const float* params, const float* table, float* grads,
                          float* dtable, int zero_dtable, int with_backward, const hpmn_outputs* out_host,
