@@ -9,7 +9,7 @@ import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TABLE = "Embedding/emb_mtx"
-NAMES = ["refgraph_amazon", "refgraph_xlong", "refgraph_dual"]
+NAMES = ["refgraph_amazon", "refgraph_xlong", "refgraph_dual", "refgraph_h64"]
 
 
 def load(name):

@@ -67,6 +67,11 @@ CASES = {
                           hop=3, user_layers=[2, 2, 3, 5, 5, 1], item_layers=[2, 2, 3, 3, 1], user_num_layers=4,
                           item_num_layers=5, user=True, item=True, l2_reg=1e-5, memory_reg=1e-5, B=3, ragged=True,
                           emb_init=False),
+    # hidden_size is a free constructor argument (hpmn.py:218-239): 64 selects the tensor-core recurrence of the CUDA path.
+    # compact: gradients stored in float32, no optimiser steps (clip + Adam are pinned by the cases above)
+    "refgraph_h64": dict(cls="Hpmn", V=150, user_dim=2, item_dim=1, user_maxlen=24, item_maxlen=4, lr=0.001, H=64, E=16,
+                         hop=3, user_layers=[2, 3, 1], item_layers=[2, 1], user_num_layers=3, item_num_layers=2, user=True,
+                         item=False, l2_reg=0.0, memory_reg=1e-4, B=5, ragged=True, emb_init=False, compact=True),
 }
 
 
@@ -132,10 +137,15 @@ def make(name, ref, tf):
             assert c["l2_reg"] == 0.0 and not np.any(gval), var.name      # connected only through 0 * l2_loss(v)
             unused.add(var.name)
         else:
-            out["grad:" + var.name] = gval
+            out["grad:" + var.name] = gval.astype(np.float32) if c.get("compact") else gval
     for k in unused:
         del out["var:" + k]
     out["unused"] = np.array(sorted(unused))
+    if c.get("compact"):
+        dst = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(dst, **out)
+        print(name, os.path.getsize(dst), "bytes;", len(g.variables), "variables; pred", out["prediction"], "loss", out["log_loss"])
+        return out
     # two optimiser steps, driven like Hpmn.train() (hpmn.py:473-483) but with keep_prob 1
     before = g.variables[table_name].numpy()
     for b in batches:

@@ -70,6 +70,49 @@ def test_cuda_path_reproduces_the_reference_graph(name, host):
     eng.close()
 
 
+def test_tensor_core_recurrence_reproduces_the_reference_graph_at_1024_steps(monkeypatch):
+    """HPMN_TCREC=1 forces the tcgen05 recurrence (normally chosen from 8192 rows per GPU) onto the XLong fixture: 1001 + 23
+    steps, 5 layers, 3xTF32 gate GEMMs through 1024 dependent steps, against the reference's own graph code"""
+    import torch
+    from hpmn_b200.engine import HpmnEngine
+    monkeypatch.setenv("HPMN_TCREC", "1")
+    z, c = G.load("refgraph_xlong")
+    sh = HpmnShape(**G.side_kwargs(c)[0])
+    p = {k: v.astype(np.float32) for k, v in G.trainables(z).items()}
+    eng = HpmnEngine(sh, device=0, memory_reg=c["memory_reg"], table=z["var:" + G.TABLE], params=p)
+    eng.forward_backward(torch.as_tensor(z["user_inp0"], device=eng.device), torch.as_tensor(z["label0"], device=eng.device))
+    torch.cuda.synchronize()
+    _close(eng.pred.cpu().numpy(), z["prediction"], "prediction")
+    _close(eng.w_hop0.cpu().numpy(), z["user_weights"], "user_weights")
+    _close(eng.scalars.cpu().numpy()[:3], [z["log_loss"], z["memory_loss"], z["cross_entropy"]], "log_loss, memory_loss, cross_entropy")
+    ref = {k: z["grad:" + k] for k in p}
+    ref[G.TABLE] = G.dense_rows(z, "grad", sh.V, sh.E)
+    got = eng.named_grads(); got[G.TABLE] = eng.dtable.cpu().numpy()
+    _grad_close(got, ref)
+    eng.close()
+
+
+def test_cuda_path_reproduces_the_reference_graph_hidden_64():
+    """hidden_size = 64: the tensor-core recurrence (tcrec.cu), the 64-lane attention kernels and the sliced weight-gradient
+    kernel against the reference's own graph code"""
+    import torch
+    from hpmn_b200.engine import HpmnEngine
+    z, c = G.load("refgraph_h64")
+    sh = HpmnShape(**G.side_kwargs(c)[0])
+    p = {k: v.astype(np.float32) for k, v in G.trainables(z).items()}
+    eng = HpmnEngine(sh, device=0, memory_reg=c["memory_reg"], table=z["var:" + G.TABLE], params=p)
+    eng.forward_backward(torch.as_tensor(z["user_inp0"], device=eng.device), torch.as_tensor(z["label0"], device=eng.device))
+    torch.cuda.synchronize()
+    _close(eng.pred.cpu().numpy(), z["prediction"], "prediction")
+    _close(eng.w_hop0.cpu().numpy(), z["user_weights"], "user_weights")
+    _close(eng.scalars.cpu().numpy()[:3], [z["log_loss"], z["memory_loss"], z["cross_entropy"]], "log_loss, memory_loss, cross_entropy")
+    ref = {k: z["grad:" + k].astype(np.float64) for k in p}
+    ref[G.TABLE] = G.dense_rows(z, "grad", sh.V, sh.E)
+    got = eng.named_grads(); got[G.TABLE] = eng.dtable.cpu().numpy()
+    _grad_close(got, ref)
+    eng.close()
+
+
 def test_cuda_path_reproduces_the_reference_graph_both_sides_with_l2():
     import torch
     from hpmn_b200.dual import HpmnDualEngine

@@ -53,6 +53,24 @@ def test_oracle_reproduces_the_reference_graph_single_side(name):
     np.testing.assert_allclose(f["pred"], z["prediction_after"], rtol=0, atol=1e-12)
 
 
+def test_oracle_reproduces_the_reference_graph_hidden_64():
+    """hidden_size = 64 (the width that selects the tensor-core recurrence on the GPU); the fixture stores its gradients in
+    float32, hence the looser gradient tolerance"""
+    z, c = G.load("refgraph_h64")
+    sh = O.OracleShape(**G.side_kwargs(c)[0])
+    p = G.trainables(z)
+    tb = z["var:" + G.TABLE].astype(np.float64)
+    f = O.forward(sh, p, tb, z["user_inp0"], z["label0"], memory_reg=c["memory_reg"], dtype=np.float64)
+    np.testing.assert_allclose(f["pred"], z["prediction"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(f["w_hop0"], z["user_weights"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose([f["logloss"], f["covreg"], f["loss"]], [z["log_loss"], z["memory_loss"], z["cross_entropy"]],
+                               rtol=1e-12, atol=1e-15)
+    g, dt = O.backward(sh, f, z["user_inp0"], z["label0"], memory_reg=c["memory_reg"])
+    for k in p:
+        np.testing.assert_allclose(g[k], z["grad:" + k], rtol=2e-6, atol=1e-10, err_msg=k)
+    np.testing.assert_allclose(dt, G.dense_rows(z, "grad", sh.V, sh.E), rtol=2e-6, atol=1e-10)
+
+
 def test_oracle_reproduces_the_reference_graph_both_sides_with_l2():
     """user=True, item=True, l2_reg != 0: concat of the two representations, memory_loss = imloss + umloss, l2 over
     every trainable including the table (hpmn.py:204-205, 452-456)"""
