@@ -102,6 +102,9 @@ def oracle_inputs(cfg, B, seed_data=1234, seed_params=4321, V_cap=None):
 NB = 8   # distinct id batches of the product arm (rotated so that no step re-reads its ids from L2)
 
 
+_RECORD = []     # the JSON line of this run (printed by main() on the real stdout)
+
+
 def make_config(cfg_name, cfg, B, world, keep_prob, ids="uniform on [1,V)"):
     """`config` of the JSON line -- identical for the product and the reference arm (same workload, same step)."""
     return {"workload": workload_name(cfg_name, cfg, B), "global_batch": B * world, "ids": ids,
@@ -156,7 +159,7 @@ def run_reference(args, cfg_name, cfg):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _RECORD.append(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -320,7 +323,7 @@ def run_product(args, cfg_name, cfg):
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": fams,
             "check": {"logloss": float(scal[0]), "covreg": float(scal[1])}}
-    print(json.dumps(line), flush=True)
+    _RECORD.append(json.dumps(line))
 
 
 def main():
@@ -340,10 +343,22 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]
-    if args.impl == "reference":
-        run_reference(args, args.config, cfg)
-    else:
-        run_product(args, args.config, cfg)
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print on file descriptor 1 while the run is set
+    # up (NCCL's version banner under torchrun) goes to stderr; the record is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args, args.config, cfg)
+        else:
+            run_product(args, args.config, cfg)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if _RECORD:
+            print(_RECORD[-1], flush=True)
 
 
 if __name__ == "__main__":
