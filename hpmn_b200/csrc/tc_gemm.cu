@@ -485,10 +485,12 @@ static void wgrad_queue_add(WgradBatch& b, int& ctas, int sms, const float* xin,
 }
 
 // Stages of the producer -> MMA ring and the shared-memory carve-out the kernel asks for.  Default: 2 stages (116 KB) and the
-// smallest carve-out that holds them, which leaves ~124 KB of the SM's unified array to L1 -- the producers' row loads
-// (x, h, r, dA rows are each read by several warps) hit there.  Measured on the XLong step: 3 stages / driver-chosen split
-// 121 us, 3 stages / maximal carve-out 162 us, 2 stages / minimal carve-out 117 us.  HPMN_WGRAD_STAGES=3 and
-// HPMN_WGRAD_CARVEOUT=<percent, -1 = driver default> override.
+// smallest carve-out that holds them (135 KB), which leaves ~120 KB of the SM's unified array to L1.  The producers keep
+// ~80 KB of global loads in flight per SM, and every 128-byte line in flight holds a line of L1 (the L1 HIT rate is 0 % either
+// way: nothing is re-read): with the maximal carve-out (233 KB) 23 KB of L1 cap the loads in flight -- ncu: DRAM throughput
+// 33 % instead of 44 %, short-scoreboard stalls 2.7 instead of 1.05 per issue, 142 instead of 105 us (profiles/r2_timeline.md).
+// In the step: 3 stages / driver-chosen split 121 us, 3 stages / maximal carve-out 162 us, 2 stages / minimal carve-out 117 us.
+// HPMN_WGRAD_STAGES=3 and HPMN_WGRAD_CARVEOUT=<percent, -1 = driver default> override.
 static int wgrad_stages() {
   static const int ns = [] { const char* e = getenv("HPMN_WGRAD_STAGES"); const int v = e ? atoi(e) : 2; return v == 3 ? 3 : 2; }();
   return ns;
