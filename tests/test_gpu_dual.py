@@ -53,7 +53,7 @@ def test_dual_memory_forward_backward_matches_autograd(industry):
     got_logit = eng.logit.cpu().numpy()
     assert np.all(np.abs(got_logit - ref_logit) <= 1e-4 * np.abs(ref_logit) + 1e-6)
     s = eng.scalars.cpu().numpy()
-    np.testing.assert_allclose(s[:3], [float(out["logloss"]), float(out["covreg"]), float(out["loss"])], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(s[:3], [out[k].item() for k in ("logloss", "covreg", "loss")], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(eng.user.w_hop0.cpu().numpy(), out["user"]["w_hop0"].detach().numpy(), rtol=1e-4, atol=1e-6)
     got = eng.named_grads()
     assert set(got) == set(params)
