@@ -35,6 +35,7 @@ struct hpmn_ctx {
   cudaEvent_t ev_fork[HPMN_MAX_LAYERS + 2];
   cudaEvent_t ev_join, ev_zero;
   bool overlap, zero_pending;
+  int wave_ctas;            // CTAs of the wavefront kernels for the step being queued (one SM each)
   void* zero_late; size_t zero_late_bytes; void* zero_grads; size_t zero_grads_bytes;   // buffers zero_behind_projection() clears
   void* fin_d2h_dst; size_t fin_d2h_bytes; cudaEvent_t fin_d2h_ev; bool fin_d2h_done;   // host path: result block copied out early
   OutCopies fin_oc; float* fin_scalars; float fin_mreg; bool fin_copies, fin_early;   // the step's finish kernel (see run_step)
@@ -318,8 +319,11 @@ static void zero_behind_projection(hpmn_ctx* ctx, cudaStream_t st) {
   cudaStreamWaitEvent(ctx->side, ctx->ev_fork[HPMN_MAX_LAYERS + 1], 0);
   Launch L{&ctx->launches, ctx->sms};
   static const int zctas = [] { const char* e = getenv("HPMN_ZERO_CTAS"); return e ? atoi(e) : 0; }();
-  // with the wavefront kernel on 128 SMs a grid of 2 CTAs per idle SM; otherwise whatever cudaMemsetAsync launches
-  const int ctas = zctas > 0 ? zctas : (ctx->wave_now ? 2 * (ctx->sms > 128 ? ctx->sms - 128 : 8) : 0);
+  // 2 CTAs per SM the wavefront kernels leave idle (they need a whole SM per CTA: registers and shared memory), so that the
+  // zeroing never sits on an SM the backward wavefront kernel is waiting for; with fewer than 8 idle SMs, or without the
+  // wavefront kernels, whatever cudaMemsetAsync launches
+  const int idle = ctx->wave_ctas > 0 ? ctx->sms - ctx->wave_ctas : 0;
+  const int ctas = zctas > 0 ? zctas : (idle >= 8 ? 2 * idle : 0);
   if (ctx->zero_grads) cudaMemsetAsync(ctx->zero_grads, 0, ctx->zero_grads_bytes, ctx->side);
   if (ctx->zero_late) {
     if (ctas > 0) launch_zero(L, ctx->zero_late, ctx->zero_late_bytes, ctas, ctx->side);
@@ -460,7 +464,7 @@ int hpmn_create(hpmn_ctx** out, int device) {
   ctx = new (std::nothrow) hpmn_ctx();
   if (!ctx) return fail(nullptr, HPMN_ENOMEM, "out of host memory");
   ctx->device = device; ctx->sms = prop.multiProcessorCount; ctx->launches = 0; ctx->err[0] = 0;
-  ctx->profile = false; ctx->pool_used = 0; ctx->wave_now = true;
+  ctx->profile = false; ctx->pool_used = 0; ctx->wave_now = true; ctx->wave_ctas = 0;
   { const char* e_tc = getenv("HPMN_NO_TC"); ctx->use_tc = !(e_tc && e_tc[0] == '1'); }
   { const char* e_w = getenv("HPMN_NO_WAVE"); ctx->use_wave = !(e_w && e_w[0] == '1'); }
   { const char* e_t = getenv("HPMN_TCREC"); ctx->tcrec_mode = e_t ? atoi(e_t) : -1;
@@ -801,8 +805,9 @@ static int run_step(hpmn_ctx* ctx, const Plan& p, const hpmn_shape* s, hpmn_hype
   // Wavefront kernels: 2 samples per CTA (1 for L > 5), one CTA per SM (shared memory).  They minimise the latency of
   // one wave; with more samples than one wave holds, the per-layer kernels (one warp per sample, ~12 resident per SM)
   // have the higher throughput (tools/microbench.py).
-  { const int nspc = d.L <= 5 ? 2 : 1; ctx->wave_now = (d.B + nspc - 1) / nspc <= ctx->sms; }
+  { const int nspc = d.L <= 5 ? 2 : 1; ctx->wave_ctas = (d.B + nspc - 1) / nspc; ctx->wave_now = ctx->wave_ctas <= ctx->sms; }
   ctx->tc_now = want_tcrec(ctx, d);
+  if (!(ctx->use_wave && ctx->wave_now && d.L <= 10) || ctx->tc_now) ctx->wave_ctas = 0;     // another memory path runs: no idle SMs to count on
   ctx->fuse_now = with_backward && ctx->fuse_mid;
   // co-running dense kernels steal issue slots from the latency-critical recurrent warps, so grouping only pays
   // once every group still fills the machine (measured: -4 % at B=256, +11 % at B=1024)
