@@ -120,22 +120,23 @@ def test_oracle_reproduces_the_reference_graph_both_sides_with_l2():
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/code/hpmn.py"), reason="the reference is only present in the build container")
-def test_fixture_is_what_the_reference_code_computes_today():
-    """Re-runs the reference's hpmn.py on the stand-in and compares with the committed amazon fixture."""
+def test_fixtures_are_what_the_reference_code_computes_today():
+    """Re-runs the reference's hpmn.py on the stand-in (one subprocess, all four cases) and compares with the committed fixtures."""
     import subprocess
     import sys
     import tempfile
     root = os.path.dirname(G.GOLD)
     code = ("import sys, numpy as np; sys.path.insert(0, %r); import make_reference_graph_fixture as M; "
-            "M.HERE = sys.argv[1]; ref, tf = M.load_reference(); M.make('refgraph_amazon', ref, tf)" % G.GOLD)
+            "M.HERE = sys.argv[1]; ref, tf = M.load_reference(); [M.make(n, ref, tf) for n in %r]" % (G.GOLD, G.NAMES))
     with tempfile.TemporaryDirectory() as tmp:
-        subprocess.run([sys.executable, "-c", code, tmp], check=True, cwd=root, stdout=subprocess.DEVNULL, timeout=300)
-        new = np.load(os.path.join(tmp, "refgraph_amazon.npz"))
-        old, _ = G.load("refgraph_amazon")
-        assert sorted(new.files) == sorted(old.files)
-        for k in old.files:
-            if old[k].dtype.kind in "fiu":
-                np.testing.assert_allclose(new[k], old[k], rtol=1e-12, atol=1e-15, err_msg=k)
+        subprocess.run([sys.executable, "-c", code, tmp], check=True, cwd=root, stdout=subprocess.DEVNULL, timeout=600)
+        for name in G.NAMES:
+            new = np.load(os.path.join(tmp, name + ".npz"))
+            old, _ = G.load(name)
+            assert sorted(new.files) == sorted(old.files), name
+            for k in old.files:
+                if old[k].dtype.kind in "fiu":
+                    np.testing.assert_allclose(new[k], old[k], rtol=1e-12, atol=1e-15, err_msg=name + ":" + k)
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/code/data_loader.py"), reason="the reference is only present in the build container")
