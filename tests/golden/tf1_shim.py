@@ -11,8 +11,11 @@ What this pins and what it does not:
   * pinned: everything hpmn.py itself decides -- the wiring of the graph, every shape / axis / slice / constant / scope
     name, the order of operations, which variables exist and which receive gradients;
   * not pinned: the arithmetic inside the TF1.4 ops, which is restated here from TF1.4's published behaviour
-    (each function below says which); the in-tree copy of the GRUCell arithmetic, code/util.py:81-110, and the in-tree
-    dynamic_rnn copy, code/rnn.py:588-807, are the anchors for the two ops that matter most.
+    (each function below says which); the in-tree copy of the GRUCell arithmetic, code/util.py:56-110, and the in-tree
+    dynamic_rnn copy, code/rnn.py:588-807, are the anchors for the two ops that matter most.  The first of the two is
+    also EXECUTED: `install()` provides the tensorflow.python.ops submodules util.py imports, and
+    tests/test_reference_graph.py::test_gru_step_equals_the_reference_in_tree_cell runs the reference's VecAttGRUCell
+    as it lies against `GRUCell.step` below and the oracle's GRU layer.
 
 Nothing in the product, the oracle or the tests imports this file; only the fixture generator does, in the build
 container.  Graph tensors declared `tf.float32` are evaluated in float64 so the fixtures are good to ~1e-15.
@@ -695,3 +698,63 @@ class _FileWriter:
 
 summary = types.SimpleNamespace(FileWriter=_FileWriter, scalar=lambda *a, **k: None, histogram=lambda *a, **k: None,
                                 merge_all=lambda: None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensorflow.python.ops.* -- only what code/util.py imports, so that the reference's in-tree copy of the GRU cell
+# arithmetic (VecAttGRUCell, util.py:56-110) can be executed as it lies (tests/test_reference_graph.py)
+# ----------------------------------------------------------------------------------------------------------------------
+class RNNCell:
+    def __init__(self, _reuse=None, **kw):
+        pass
+
+
+class _Linear:
+    """tensorflow.python.ops.rnn_cell_impl._Linear [TF1.4]: concat(args, 1) @ kernel (+ bias); `kernel` [sum of the args' widths,
+    output_size] with the scope's default initializer unless one is given, `bias` [output_size] initialised to 0 unless
+    a bias_initializer is given; both created in the variable scope that is current at construction."""
+
+    def __init__(self, args, output_size, build_bias, bias_initializer=None, kernel_initializer=None):
+        args = list(args) if isinstance(args, (list, tuple)) else [args]
+        total = sum(int(a.probe.shape[1]) for a in args)
+        self.kernel = get_variable("kernel", [total, int(output_size)], initializer=kernel_initializer)
+        self.bias = None
+        if build_bias:
+            self.bias = get_variable("bias", [int(output_size)],
+                                     initializer=bias_initializer if bias_initializer is not None else constant_initializer(0.0))
+
+    def __call__(self, args):
+        args = list(args) if isinstance(args, (list, tuple)) else [args]
+        res = matmul(concat(args, 1), self.kernel)
+        return res + self.bias if self.bias is not None else res
+
+
+Tensor.dtype = float32      # `inputs.dtype` (util.py:84)
+
+
+def install(sys_modules):
+    """sys.modules entries for `import tensorflow` and the tensorflow.python.ops submodules code/util.py imports"""
+    import sys as _sys
+    me = _sys.modules[__name__]
+    ns = types.SimpleNamespace
+    mods = {
+        "tensorflow": me,
+        "tensorflow.python": types.ModuleType("tensorflow.python"),
+        "tensorflow.python.ops": types.ModuleType("tensorflow.python.ops"),
+        "tensorflow.python.ops.array_ops": types.ModuleType("array_ops"),
+        "tensorflow.python.ops.init_ops": types.ModuleType("init_ops"),
+        "tensorflow.python.ops.math_ops": types.ModuleType("math_ops"),
+        "tensorflow.python.ops.variable_scope": types.ModuleType("variable_scope"),
+        "tensorflow.python.ops.rnn_cell": types.ModuleType("rnn_cell"),
+        "tensorflow.python.ops.rnn_cell_impl": types.ModuleType("rnn_cell_impl"),
+    }
+    a = mods["tensorflow.python.ops.array_ops"]; a.split, a.concat = split, concat
+    i = mods["tensorflow.python.ops.init_ops"]
+    i.constant_initializer = lambda value=0.0, dtype=None: constant_initializer(value)
+    m = mods["tensorflow.python.ops.math_ops"]; m.sigmoid, m.tanh, m.matmul = sigmoid, tanh, matmul
+    v = mods["tensorflow.python.ops.variable_scope"]; v.variable_scope, v.get_variable = variable_scope, get_variable
+    r = mods["tensorflow.python.ops.rnn_cell"]; r.RNNCell, r.GRUCell = RNNCell, GRUCell
+    r.__all__ = ["RNNCell", "GRUCell"]
+    mods["tensorflow.python.ops.rnn_cell_impl"]._Linear = _Linear
+    sys_modules.update(mods)
+    return me

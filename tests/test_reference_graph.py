@@ -159,3 +159,69 @@ def test_dataloader_equals_the_reference_loader_on_the_reference_dataset_sample(
         assert ia == ib
         assert list(da[0]) == list(db[0]) and list(da[2]) == list(db[2]) and list(da[4]) == list(db[4])
         assert np.array_equal(np.asarray(da[1]), np.asarray(db[1])) and np.array_equal(np.asarray(da[3]), np.asarray(db[3]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/code/util.py"), reason="the reference is only present in the build container")
+def test_gru_step_equals_the_reference_in_tree_cell():
+    """code/util.py:56-110 (VecAttGRUCell) is the reference's in-tree copy of the TF1.4 GRUCell arithmetic: gates =
+    sigmoid(_Linear([x, h])) split r | u, candidate on [x, r * h], bias of the gates initialised to 1, h' = u h + (1 - u) c
+    (its one addition, `u = (1 - att_score) * u`, is the identity for att_score = 0).  Executed as it lies on the TF1-API
+    stand-in -- only `_Linear` (concat, matmul, bias) is supplied -- it must agree with the cell the stand-in's dynamic_rnn
+    runs and with the oracle's GRU layer, over several steps."""
+    import importlib.util
+    import pickle
+    import subprocess
+    import sys
+    code = r'''
+import sys, pickle, importlib.util
+import numpy as np
+sys.path.insert(0, %r)
+import tf1_shim as tf
+tf.install(sys.modules)
+sys.modules["cPickle"] = pickle
+spec = importlib.util.spec_from_file_location("reference_util", "/root/reference/code/util.py")
+util = importlib.util.module_from_spec(spec); spec.loader.exec_module(util)
+rng = np.random.default_rng(3)
+B, D, H, T = 4, 6, 5, 7
+x = rng.normal(size=(B, T, D)); 
+cell = util.VecAttGRUCell(H)
+xs = [tf.constant(x[:, t]) for t in range(T)]
+h = tf.constant(np.zeros((B, H)))
+outs = []
+with tf.variable_scope("rnn"):
+    with tf.variable_scope("gru_cell"):
+        for t in range(T):
+            _, h = cell(xs[t], h, 0.0)
+            outs.append(h)
+g = tf._g()
+init = {k: v.numpy() for k, v in g.variables.items()}
+for k, v in g.variables.items():      # away from the initial values (bias 1 / 0), keeping what the cell created
+    v.value.data += __import__("torch").as_tensor(rng.normal(scale=0.3, size=tuple(v.value.shape)))
+sess = tf.Session()
+hs = np.stack(sess.run(outs), axis=1)
+var = {k: v.numpy() for k, v in g.variables.items()}
+pickle.dump({"x": x, "hs": hs, "var": var, "init": init}, open(sys.argv[1], "wb"))
+''' % G.GOLD
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "cell.pkl")
+        subprocess.run([sys.executable, "-c", code, out], check=True, timeout=300)
+        with open(out, "rb") as f:
+            r = pickle.load(f)
+    var = r["var"]
+    assert sorted(var) == ["rnn/gru_cell/candidate/bias", "rnn/gru_cell/candidate/kernel", "rnn/gru_cell/gates/bias",
+                           "rnn/gru_cell/gates/kernel"]
+    Wg, bg = var["rnn/gru_cell/gates/kernel"], var["rnn/gru_cell/gates/bias"]
+    Wc, bc = var["rnn/gru_cell/candidate/kernel"], var["rnn/gru_cell/candidate/bias"]
+    assert Wg.shape == (6 + 5, 10) and Wc.shape == (6 + 5, 5)
+    assert np.all(r["init"]["rnn/gru_cell/gates/bias"] == 1.0) and np.all(r["init"]["rnn/gru_cell/candidate/bias"] == 0.0)   # util.py:84-86
+    hs_oracle = O.gru_layer_fwd(r["x"], Wg, bg, Wc, bc)[0]
+    np.testing.assert_allclose(hs_oracle, r["hs"], rtol=0, atol=1e-14)
+    # and the cell the stand-in's dynamic_rnn uses for the fixtures
+    sys.path.insert(0, G.GOLD)
+    import torch
+    import tf1_shim
+    h = torch.zeros(4, 5, dtype=torch.float64)
+    for t in range(7):
+        h = tf1_shim.GRUCell.step(torch.as_tensor(r["x"][:, t]), h, *(torch.as_tensor(a) for a in (Wg, bg, Wc, bc)))
+        np.testing.assert_allclose(h.numpy(), r["hs"][:, t], rtol=0, atol=1e-14)
