@@ -66,9 +66,11 @@ def main():
             for i in range(args.steps):
                 step(i)
         torch.cuda.synchronize()
-    tmp = tempfile.mktemp(suffix=".json")
-    prof.export_chrome_trace(tmp)
-    ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")]
+    with tempfile.TemporaryDirectory() as tmpdir:
+        tmp = os.path.join(tmpdir, "trace.json")
+        prof.export_chrome_trace(tmp)
+        with open(tmp) as f:
+            ev = [e for e in json.load(f)["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")]
     ev.sort(key=lambda e: e["ts"])
     # one steady-state step: from the 2nd-to-last gather to the last gather
     gathers = [i for i, e in enumerate(ev) if "gather_fwd" in e["name"]]
